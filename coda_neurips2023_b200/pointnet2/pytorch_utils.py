@@ -1,0 +1,148 @@
+"""Shared 1x1-conv MLP blocks with the reference's module tree.
+
+Mirrors the public names and, more importantly, the *parameter paths* of
+third_party_pointnet2/pointnet2/pytorch_utils.py (``layer{i}.conv.weight``,
+``layer{i}.bn.bn.{weight,bias,running_mean,running_var,num_batches_tracked}``) so
+that checkpoints written by the reference load unchanged.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch.nn as nn
+
+
+class _NormWrap(nn.Sequential):
+    """`bn` submodule holding a `bn` child: gives the `.bn.bn.weight` key path
+    (reference pytorch_utils.py:36-44); affine initialised to (1, 0)."""
+
+    def __init__(self, channels: int, norm_cls, name: str = ""):
+        super().__init__()
+        self.add_module(name + "bn", norm_cls(channels))
+        nn.init.constant_(self[0].weight, 1.0)
+        nn.init.constant_(self[0].bias, 0.0)
+
+
+class BatchNorm1d(_NormWrap):
+    def __init__(self, in_size: int, *, name: str = ""):
+        super().__init__(in_size, nn.BatchNorm1d, name)
+
+
+class BatchNorm2d(_NormWrap):
+    def __init__(self, in_size: int, name: str = ""):
+        super().__init__(in_size, nn.BatchNorm2d, name)
+
+
+class BatchNorm3d(_NormWrap):
+    def __init__(self, in_size: int, name: str = ""):
+        super().__init__(in_size, nn.BatchNorm3d, name)
+
+
+class _ConvBlock(nn.Sequential):
+    """conv (+ bn) (+ activation), or pre-activation order; a conv bias exists
+    only when there is no batch norm (reference pytorch_utils.py:65-118)."""
+
+    _conv_cls = None
+    _norm_cls = None
+    _default_kernel: Sequence[int] | int = 1
+
+    def __init__(self, in_size: int, out_size: int, *, kernel_size=None, stride=None, padding=None,
+                 activation=nn.ReLU(inplace=True), bn: bool = False, init=nn.init.kaiming_normal_,
+                 bias: bool = True, preact: bool = False, name: str = ""):
+        super().__init__()
+        nd = {nn.Conv1d: 1, nn.Conv2d: 2, nn.Conv3d: 3}[self._conv_cls]
+        if kernel_size is None:
+            kernel_size = 1 if nd == 1 else (1,) * nd
+        if stride is None:
+            stride = 1 if nd == 1 else (1,) * nd
+        if padding is None:
+            padding = 0 if nd == 1 else (0,) * nd
+        conv = self._conv_cls(in_size, out_size, kernel_size=kernel_size, stride=stride,
+                              padding=padding, bias=bias and not bn)
+        init(conv.weight)
+        if conv.bias is not None:
+            nn.init.constant_(conv.bias, 0.0)
+        norm = self._norm_cls(in_size if preact else out_size) if bn else None
+        tail = []
+        if norm is not None:
+            tail.append((name + "bn", norm))
+        if activation is not None:
+            tail.append((name + "activation", activation))
+        order = tail + [(name + "conv", conv)] if preact else [(name + "conv", conv)] + tail
+        for key, mod in order:
+            self.add_module(key, mod)
+
+
+class Conv1d(_ConvBlock):
+    _conv_cls = nn.Conv1d
+    _norm_cls = BatchNorm1d
+
+
+class Conv2d(_ConvBlock):
+    _conv_cls = nn.Conv2d
+    _norm_cls = BatchNorm2d
+
+
+class Conv3d(_ConvBlock):
+    _conv_cls = nn.Conv3d
+    _norm_cls = BatchNorm3d
+
+
+class SharedMLP(nn.Sequential):
+    """Stack of 1x1 Conv2d blocks: `layer0`, `layer1`, ... (reference
+    pytorch_utils.py:8-33)."""
+
+    def __init__(self, args: List[int], *, bn: bool = False, activation=nn.ReLU(inplace=True),
+                 preact: bool = False, first: bool = False, name: str = ""):
+        super().__init__()
+        for i in range(len(args) - 1):
+            plain = first and preact and i == 0  # the very first pre-act block has no bn/act
+            self.add_module(
+                f"{name}layer{i}",
+                Conv2d(args[i], args[i + 1], bn=bn and not plain,
+                       activation=None if plain else activation, preact=preact))
+
+
+class FC(nn.Sequential):
+    """Linear (+ BatchNorm1d) (+ activation) (reference pytorch_utils.py:219-254)."""
+
+    def __init__(self, in_size: int, out_size: int, *, activation=nn.ReLU(inplace=True),
+                 bn: bool = False, init=None, preact: bool = False, name: str = ""):
+        super().__init__()
+        fc = nn.Linear(in_size, out_size, bias=not bn)
+        if init is not None:
+            init(fc.weight)
+        if not bn:
+            nn.init.constant_(fc.bias, 0.0)
+        tail = []
+        if bn:
+            tail.append((name + "bn", BatchNorm1d(in_size if preact else out_size)))
+        if activation is not None:
+            tail.append((name + "activation", activation))
+        order = tail + [(name + "fc", fc)] if preact else [(name + "fc", fc)] + tail
+        for key, mod in order:
+            self.add_module(key, mod)
+
+
+def set_bn_momentum_default(bn_momentum):
+    def fn(m):
+        if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)):
+            m.momentum = bn_momentum
+    return fn
+
+
+class BNMomentumScheduler:
+    """Applies `bn_lambda(epoch)` as the momentum of every BatchNorm in `model`."""
+
+    def __init__(self, model, bn_lambda, last_epoch: int = -1, setter=set_bn_momentum_default):
+        if not isinstance(model, nn.Module):
+            raise RuntimeError(f"Class '{type(model).__name__}' is not a PyTorch nn Module")
+        self.model, self.setter, self.lmbd = model, setter, bn_lambda
+        self.step(last_epoch + 1)
+        self.last_epoch = last_epoch
+
+    def step(self, epoch: Optional[int] = None):
+        if epoch is None:
+            epoch = self.last_epoch + 1
+        self.last_epoch = epoch
+        self.model.apply(self.setter(self.lmbd(epoch)))
