@@ -95,7 +95,7 @@ fps_cluster_kernel(int n, int m, int bs_log2, int R, int cl_log2,
       y = __ldg(xyz + (size_t)k * 3 + 1);
       z = __ldg(xyz + (size_t)k * 3 + 2);
       // sampling_gpu.cu:103-104 (mag compared against the double constant 1e-3)
-      const float mag = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+      const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
       valid = !((double)mag <= 1e-3);
     }
     px[i] = x; py[i] = y; pz[i] = z;
@@ -130,7 +130,7 @@ fps_cluster_kernel(int n, int m, int bs_log2, int R, int cl_log2,
       const float dx = __fsub_rn(px[i], cx), dy = __fsub_rn(py[i], cy),
                   dz = __fsub_rn(pz[i], cz);
       const float d =
-          __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+          __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
       const float t = fminf(d, pt[i]);
       pt[i] = t;
       if (t > best) { best = t; bi = i; }  // ascending position => smallest p kept
@@ -210,7 +210,7 @@ fps_generic_kernel(int n, int m, int bs_log2, int R, const float *__restrict__ x
   const int bs_mask = (1 << bs_log2) - 1;
   for (int k = tid; k < n; k += 1024) {
     const float x = xyz[k * 3], y = xyz[k * 3 + 1], z = xyz[k * 3 + 2];
-    const float mag = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+    const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
     temp[k] = ((double)mag <= 1e-3) ? -1.0f : 1e10f;
   }
   if (tid == 0) idx[0] = 0;
@@ -226,7 +226,7 @@ fps_generic_kernel(int n, int m, int bs_log2, int R, const float *__restrict__ x
       if (t >= 0.f) {
         const float dx = __fsub_rn(xyz[k * 3], cx), dy = __fsub_rn(xyz[k * 3 + 1], cy),
                     dz = __fsub_rn(xyz[k * 3 + 2], cz);
-        const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+        const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
         t = fminf(d, t);
         temp[k] = t;
         const int c = k & bs_mask;
@@ -338,9 +338,9 @@ ball_query_kernel(int n, int m, float radius2, int nsample, int normalize,
         bool hit = false;
         if (k < tn) {
           const float x = tile[k * 3], y = tile[k * 3 + 1], z = tile[k * 3 + 2];
-          // ball_query_gpu.cu:34-35: (new_x - x)^2 + ... as FMUL, FFMA, FFMA
+          // ball_query_gpu.cu:34-35: (new_x - x)^2 + ... -> FMUL(dy,dy), FFMA(dx,dx,.), FFMA(dz,dz,.) (reference SASS)
           const float dx = __fsub_rn(cxv, x), dy = __fsub_rn(cyv, y), dz = __fsub_rn(czv, z);
-          const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+          const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
           hit = d2 < radius2;
         }
         const unsigned mask = __ballot_sync(0xffffffffu, hit);
@@ -465,7 +465,7 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown,
     for (int k = 0; k < tn; ++k) {
       const float dx = __fsub_rn(ux, tile[k * 3]), dy = __fsub_rn(uy, tile[k * 3 + 1]),
                   dz = __fsub_rn(uz, tile[k * 3 + 2]);
-      const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+      const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
       const int kk = base + k;
       if (d < b1) {
         b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = kk;
@@ -499,9 +499,9 @@ __global__ void three_interpolate_kernel(int c, int m, int n, int c_per_block,
   const int l0 = blockIdx.y * c_per_block, l1 = min(c, l0 + c_per_block);
   for (int l = l0; l < l1; ++l) {
     const float *p = points + ((size_t)b * c + l) * m;
-    // interpolate_gpu.cu:101-102: p1*w1 + p2*w2 + p3*w3 -> FMUL, FFMA, FFMA
+    // interpolate_gpu.cu:101-102: p1*w1 + p2*w2 + p3*w3 -> FMUL(p2,w2), FFMA(p1,w1), FFMA(p3,w3)
     out[((size_t)b * c + l) * n + j] =
-        __fmaf_rn(__ldg(p + i3), w3, __fmaf_rn(__ldg(p + i2), w2, __fmul_rn(__ldg(p + i1), w1)));
+        __fmaf_rn(__ldg(p + i3), w3, __fmaf_rn(__ldg(p + i1), w1, __fmul_rn(__ldg(p + i2), w2)));
   }
 }
 

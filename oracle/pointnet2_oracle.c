@@ -15,8 +15,10 @@
  *
  * Each function simulates the reference kernel thread by thread, so that the
  * tie rules, the skip rule and the fp32 rounding (explicit fmaf in the order
- * nvcc's default --fmad=true contraction produces, verified in the SASS, see
- * SURVEY.md section 2a) are those of the reference, not of a "clean" algorithm.
+ * nvcc's default --fmad=true contraction produces -- read off the SASS of the
+ * reference objects, oracle/_ref/obj/ (one .o per source): for a*a + b*b + c*c it is
+ * FMUL(b,b), FFMA(a,a,.), FFMA(c,c,.)) are those of the reference, not of a
+ * "clean" algorithm.
  * Compile with -ffp-contract=off so the host compiler adds no contraction of
  * its own.
  *
@@ -38,10 +40,13 @@ int oracle_opt_n_threads(int work_size) {
 
 static float sqdist_pt_minus_ref(float x2, float y2, float z2, float x1,
                                  float y1, float z1) {
-  /* src/sampling_gpu.cu:106-107: (x2-x1)*(x2-x1)+(y2-y1)*(y2-y1)+(z2-z1)*(z2-z1)
-   * contracted by nvcc to FMUL, FFMA, FFMA */
+  /* src/sampling_gpu.cu:106-107: (x2-x1)*(x2-x1)+(y2-y1)*(y2-y1)+(z2-z1)*(z2-z1).
+   * nvcc (--fmad=true) contracts a*a + b*b + c*c as FMUL(b,b); FFMA(a,a,.);
+   * FFMA(c,c,.) -- read off the SASS of the reference build for sm_100
+   * (cuobjdump -sass oracle/_ref/obj/sampling_gpu.cu.o): the SECOND product is
+   * the plain multiply. */
   const float dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
-  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
 /*
@@ -73,7 +78,7 @@ void oracle_furthest_point_sampling(int b, int n, int m, const float *dataset,
         for (int k = tid; k < n; k += bs) {
           const float x2 = ds[k * 3 + 0], y2 = ds[k * 3 + 1],
                       z2 = ds[k * 3 + 2];
-          const float mag = fmaf(z2, z2, fmaf(y2, y2, x2 * x2)); /* :103 */
+          const float mag = fmaf(z2, z2, fmaf(x2, x2, y2 * y2)); /* :103, same contraction */
           if ((double)mag <= 1e-3) continue;                   /* :104 */
           const float d = sqdist_pt_minus_ref(x2, y2, z2, x1, y1, z1);
           const float d2 = fminf(d, temp[k]); /* :109 */
@@ -142,9 +147,9 @@ void oracle_ball_query(int b, int n, int m, float radius, int nsample,
       const float nx = C[j * 3 + 0], ny = C[j * 3 + 1], nz = C[j * 3 + 2];
       for (int k = 0, cnt = 0; k < n && cnt < nsample; ++k) {
         const float x = X[k * 3 + 0], y = X[k * 3 + 1], z = X[k * 3 + 2];
-        /* :34-35 (new_x-x)^2+(new_y-y)^2+(new_z-z)^2 -> FMUL, FFMA, FFMA */
+        /* :34-35 (new_x-x)^2+(new_y-y)^2+(new_z-z)^2 -> FMUL(dy), FFMA(dx), FFMA(dz) */
         const float dx = nx - x, dy = ny - y, dz = nz - z;
-        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const float d2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
         if (d2 < radius2) {
           if (cnt == 0)
             for (int l = 0; l < nsample; ++l) I[j * nsample + l] = k; /* :37-41 */
@@ -200,7 +205,7 @@ void oracle_three_nn(int b, int n, int m, const float *unknown,
       for (int k = 0; k < m; ++k) {
         const float x = K[k * 3 + 0], y = K[k * 3 + 1], z = K[k * 3 + 2];
         const float dx = ux - x, dy = uy - y, dz = uz - z;
-        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx)); /* :36 */
+        const float d = fmaf(dz, dz, fmaf(dx, dx, dy * dy)); /* :36 */
         if (d < best1) {
           best3 = best2; besti3 = besti2;
           best2 = best1; besti2 = besti1;
@@ -220,7 +225,7 @@ void oracle_three_nn(int b, int n, int m, const float *unknown,
 }
 
 /* src/interpolate_gpu.cu:75-104 three_interpolate_kernel:
- * p1*w1 + p2*w2 + p3*w3 -> FMUL, FFMA, FFMA (left to right) */
+ * p1*w1 + p2*w2 + p3*w3 -> FMUL(p2,w2); FFMA(p1,w1,.); FFMA(p3,w3,.) (SASS) */
 void oracle_three_interpolate(int b, int c, int m, int n, const float *points,
                               const int *idx, const float *weight, float *out) {
   for (int bi = 0; bi < b; ++bi)
@@ -230,7 +235,7 @@ void oracle_three_interpolate(int b, int c, int m, int n, const float *points,
         const int *ii = idx + ((size_t)bi * n + j) * 3;
         const float *p = points + ((size_t)bi * c + l) * m;
         out[((size_t)bi * c + l) * n + j] =
-            fmaf(p[ii[2]], w[2], fmaf(p[ii[1]], w[1], p[ii[0]] * w[0]));
+            fmaf(p[ii[2]], w[2], fmaf(p[ii[0]], w[0], p[ii[1]] * w[1]));
       }
 }
 

@@ -33,8 +33,9 @@ def fps_position_space(xyz: np.ndarray, m: int) -> np.ndarray:
     for bi in range(b):
         p = xyz[bi].astype(np.float32)
         x, y, z = p[:, 0], p[:, 1], p[:, 2]
-        mag = np.float32(x * x)
-        mag = (y.astype(np.float64) * y.astype(np.float64) + mag.astype(np.float64)).astype(np.float32)  # fma
+        # reference SASS order: FMUL(y,y); FFMA(x,x,.); FFMA(z,z,.)
+        mag = np.float32(y * y)
+        mag = (x.astype(np.float64) * x.astype(np.float64) + mag.astype(np.float64)).astype(np.float32)  # fma
         mag = (z.astype(np.float64) * z.astype(np.float64) + mag.astype(np.float64)).astype(np.float32)
         valid = ~(mag.astype(np.float64) <= 1e-3)
         temp = np.where(valid, np.float32(1e10), np.float32(-1.0)).astype(np.float32)
@@ -43,8 +44,8 @@ def fps_position_space(xyz: np.ndarray, m: int) -> np.ndarray:
             d = p - p[old]
             dx, dy, dz = d[:, 0], d[:, 1], d[:, 2]
             # fp32 FMA emulated in float64 (exact for a single product-sum of fp32 operands)
-            acc = np.float32(dx * dx)
-            acc = (dy.astype(np.float64) * dy + acc.astype(np.float64)).astype(np.float32)
+            acc = np.float32(dy * dy)
+            acc = (dx.astype(np.float64) * dx + acc.astype(np.float64)).astype(np.float32)
             acc = (dz.astype(np.float64) * dz + acc.astype(np.float64)).astype(np.float32)
             temp = np.where(valid, np.minimum(acc, temp), temp).astype(np.float32)
             if not valid.any():
