@@ -42,6 +42,8 @@ def lib() -> ctypes.CDLL:
         _lib = ctypes.CDLL(str(LIB_PATH))
         _lib.coda_status_string.restype = ctypes.c_char_p
         _lib.coda_status_string.argtypes = [ctypes.c_int]
+        if hasattr(_lib, "coda_layer_norm_bwd_scratch"):
+            _lib.coda_layer_norm_bwd_scratch.restype = ctypes.c_longlong
         missing = [s for s in declared_symbols() if not hasattr(_lib, s)]
         if missing:
             raise CodaError(f"{LIB_PATH} does not export: {missing}")

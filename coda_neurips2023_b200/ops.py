@@ -1,0 +1,196 @@
+"""torch-facing wrappers (autograd where needed) around the C-ABI kernels of
+include/coda_detr.h and include/coda_attention.h.  Every function here launches
+hand-written sm_100a code on the current stream; none has a CPU or PyTorch
+fallback -- a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from ._lib import check, lib, ptr, stream_of
+
+_i = ctypes.c_int
+_ll = ctypes.c_longlong
+_f = ctypes.c_float
+
+
+def _need_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: CPU not supported (coda_b200 kernels are CUDA-only)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------- LayerNorm
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        _need_cuda(x, "layer_norm")
+        xc = _f32c(x)
+        c = xc.shape[-1]
+        rows = xc.numel() // c
+        y = torch.empty_like(xc)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            st = lib().coda_layer_norm_fwd(_ll(rows), _i(c), _f(eps), ptr(xc), ptr(weight), ptr(bias), ptr(y),
+                                           ptr(mean), ptr(rstd), stream_of(x))
+        check(st, "layer_norm_fwd")
+        ctx.save_for_backward(xc, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, weight, mean, rstd = ctx.saved_tensors
+        dyc = _f32c(dy)
+        c = xc.shape[-1]
+        rows = xc.numel() // c
+        dx = torch.empty_like(xc)
+        dgamma = torch.empty_like(weight)
+        dbeta = torch.empty_like(weight)
+        nscratch = lib().coda_layer_norm_bwd_scratch(_ll(rows), _i(c))
+        partial = torch.empty(max(int(nscratch), 1), dtype=torch.float32, device=xc.device)
+        with torch.cuda.device(xc.device):
+            st = lib().coda_layer_norm_bwd(_ll(rows), _i(c), ptr(dyc), ptr(xc), ptr(weight), ptr(mean), ptr(rstd),
+                                           ptr(dx), ptr(dgamma), ptr(dbeta), ptr(partial), stream_of(xc))
+        check(st, "layer_norm_bwd")
+        return dx, dgamma, dbeta, None
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """LayerNorm over the last dim (multiple of 128, <= 1024); fp32."""
+    return _LayerNorm.apply(x, weight, bias, float(eps))
+
+
+class LayerNorm(torch.nn.LayerNorm):
+    """nn.LayerNorm with the same parameters / state-dict keys, running the
+    warp-per-row kernel (reference NORM_DICT["ln"], models/helpers.py:27-32)."""
+
+    def forward(self, x):
+        return layer_norm(x, self.weight, self.bias, self.eps)
+
+
+# --------------------------------------------------------------------------- softmax
+def softmax_rows(x: torch.Tensor, log: bool = False) -> torch.Tensor:
+    """softmax / log-softmax over the last dimension (no autograd)."""
+    _need_cuda(x, "softmax_rows")
+    xc = _f32c(x.detach())
+    c = xc.shape[-1]
+    y = torch.empty_like(xc)
+    with torch.cuda.device(x.device):
+        st = lib().coda_softmax_rows(_ll(xc.numel() // c), _i(c), _i(1 if log else 0), ptr(xc), ptr(y), stream_of(x))
+    check(st, "softmax_rows")
+    return y
+
+
+# --------------------------------------------------------------------------- Fourier pos-enc
+@torch.no_grad()
+def fourier_pos_embed(xyz: torch.Tensor, gauss_B: torch.Tensor, d_out: int, input_range=None) -> torch.Tensor:
+    """xyz (B, N, 3) -> (B, 2*d_out, N) = [sin | cos](2 pi x_hat @ gauss_B[:, :d_out]);
+    x_hat is xyz mapped to [0, 1] by `input_range` = [min (B, 3), max (B, 3)] if given."""
+    _need_cuda(xyz, "fourier_pos_embed")
+    xc = _f32c(xyz)
+    gb = _f32c(gauss_B)
+    b, n, _ = xc.shape
+    out = torch.empty((b, 2 * d_out, n), dtype=torch.float32, device=xyz.device)
+    rmin = rmax = None
+    if input_range is not None:
+        rmin, rmax = _f32c(input_range[0]), _f32c(input_range[1])
+    with torch.cuda.device(xyz.device):
+        st = lib().coda_fourier_pos_embed(_i(b), _i(n), _i(d_out), _i(gb.shape[1]), _i(0 if rmin is None else 1),
+                                          ptr(xc), ptr(rmin), ptr(rmax), ptr(gb), ptr(out), stream_of(xyz))
+    check(st, "fourier_pos_embed")
+    return out
+
+
+# --------------------------------------------------------------------------- GIoU / matcher
+@torch.no_grad()
+def giou3d(corners1: torch.Tensor, corners2: torch.Tensor, nums_k2: torch.Tensor, rotated,
+           rot_k2_limit: int | None = None) -> torch.Tensor:
+    """(B, K1, 8, 3), (B, K2, 8, 3), (B,) -> generalised IoU (B, K1, K2).
+    `rotated` is a bool, or a 1-element device tensor (read by the kernel: no host sync)."""
+    _need_cuda(corners1, "giou3d")
+    c1, c2 = _f32c(corners1), _f32c(corners2)
+    b, k1, k2 = c1.shape[0], c1.shape[1], c2.shape[1]
+    nk = nums_k2.to(device=c1.device, dtype=torch.int32).contiguous()
+    out = torch.empty((b, k1, k2), dtype=torch.float32, device=c1.device)
+    lim = k2 if rot_k2_limit is None else int(rot_k2_limit)
+    rdev = None
+    if isinstance(rotated, torch.Tensor):
+        rdev = rotated.to(device=c1.device, dtype=torch.int32).reshape(1).contiguous()
+        rotated = False
+    with torch.cuda.device(c1.device):
+        st = lib().coda_giou3d(_i(b), _i(k1), _i(k2), _i(1 if rotated else 0), ptr(rdev), _i(lim), ptr(c1), ptr(c2),
+                               ptr(nk), ptr(out), stream_of(c1))
+    check(st, "giou3d")
+    return out
+
+
+@torch.no_grad()
+def hungarian(cost: torch.Tensor, nactual: torch.Tensor):
+    """cost (B, nprop, ngt) fp32, nactual (B,) -> (per_prop_gt_inds int64 (B, nprop),
+    proposal_matched_mask fp32 (B, nprop)); same assignment as scipy's
+    linear_sum_assignment on cost[b, :, :nactual[b]]."""
+    _need_cuda(cost, "hungarian")
+    cc = _f32c(cost)
+    b, nprop, ngt = cc.shape
+    na = nactual.to(device=cc.device, dtype=torch.int32).contiguous()
+    inds = torch.empty((b, nprop), dtype=torch.int64, device=cc.device)
+    mask = torch.empty((b, nprop), dtype=torch.float32, device=cc.device)
+    with torch.cuda.device(cc.device):
+        st = lib().coda_hungarian(_i(b), _i(nprop), _i(ngt), ptr(cc), ptr(na), ptr(inds), ptr(mask), stream_of(cc))
+    check(st, "hungarian")
+    return inds, mask
+
+
+# --------------------------------------------------------------------------- attention
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, nhead: int, dropout_p: float = 0.0,
+              training: bool = False, causal: bool = False) -> torch.Tensor:
+    """Multi-head scaled-dot-product attention on projected, sequence-first tensors.
+
+    q (Lq, B, E), k / v (Lk, B, E) -> (Lq, B, E).  The scale 1/sqrt(E/nhead) is applied to
+    q; the forward kernel never materialises the probabilities in HBM.
+    """
+    _need_cuda(q, "attention")
+    from . import attention_sm100  # tcgen05 kernels (include/coda_attention.h)
+
+    return attention_sm100.attention(q, k, v, nhead, dropout_p, training, causal)
+
+
+# --------------------------------------------------------------------------- CLIP crops
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+@torch.no_grad()
+def crop_resize_normalize(images: torch.Tensor, scene: torch.Tensor, boxes: torch.Tensor, valid: torch.Tensor,
+                          res: int, dtype=torch.float16, mean=CLIP_MEAN, std=CLIP_STD) -> torch.Tensor:
+    """images (B, H, W, 3) uint8, scene (N,) int32, boxes (N, 4) int32 [xmin, ymin, xmax, ymax],
+    valid (N,) bool -> (N, 3, res, res) CLIP-normalised crops (white-padded to square, antialiased
+    bicubic resize with torchvision's uint8 semantics)."""
+    _need_cuda(images, "crop_resize_normalize")
+    if images.dtype != torch.uint8:
+        raise RuntimeError("images must be uint8 (HWC)")
+    img = images.contiguous()
+    nimg, h, w, _ = img.shape
+    n = boxes.shape[0]
+    sc = scene.to(torch.int32).contiguous()
+    bx = boxes.to(torch.int32).contiguous()
+    vd = valid.to(torch.uint8).contiguous()
+    if dtype not in (torch.float16, torch.float32):
+        raise RuntimeError("output dtype must be float16 or float32")
+    out = torch.empty((n, 3, res, res), dtype=dtype, device=img.device)
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    with torch.cuda.device(img.device):
+        st = lib().coda_crop_resize_normalize(_i(nimg), _i(h), _i(w), _i(n), _i(res), ptr(img), ptr(sc), ptr(bx),
+                                              ptr(vd), m, s, _i(1 if dtype == torch.float16 else 0), ptr(out),
+                                              stream_of(img))
+    check(st, "crop_resize_normalize")
+    return out

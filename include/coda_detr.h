@@ -1,0 +1,99 @@
+/*
+ * coda_detr.h -- C-ABI of the warp-primitive kernels of the 3DETR encoder /
+ * decoder, box geometry and matcher (everything on the training-step path that
+ * is not a dense contraction; the tensor-core attention is in coda_attention.h).
+ *
+ * Conventions as in coda_pointnet2.h: raw device pointers, dense row-major fp32
+ * unless stated, `void *stream` is a cudaStream_t, int status (0 = ok).
+ * The reference has no native code for these ops -- it reaches them through
+ * PyTorch; each entry cites the Python it replaces.
+ */
+#ifndef CODA_DETR_H
+#define CODA_DETR_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/*
+ * LayerNorm over the last dimension, one warp per row.
+ *   replaces nn.LayerNorm in TransformerEncoderLayer / TransformerDecoderLayer
+ *   (models/transformer.py:461-479, :556-580; NORM_DICT["ln"], models/helpers.py:27-32)
+ *   x, y (rows, c); gamma, beta (c); mean, rstd (rows) saved for backward.
+ *   c must be a multiple of 128 and <= 1024.
+ */
+int coda_layer_norm_fwd(long long rows, int c, float eps, const float *x,
+                        const float *gamma, const float *beta, float *y,
+                        float *mean, float *rstd, void *stream);
+/*
+ *   dx (rows, c) may alias dy.  dgamma / dbeta (c) are fully written.
+ *   `partial` is caller-provided scratch of coda_layer_norm_bwd_scratch(rows, c)
+ *   floats (block partial sums, reduced deterministically).
+ */
+long long coda_layer_norm_bwd_scratch(long long rows, int c);
+int coda_layer_norm_bwd(long long rows, int c, const float *dy, const float *x,
+                        const float *gamma, const float *mean, const float *rstd,
+                        float *dx, float *dgamma, float *dbeta, float *partial,
+                        void *stream);
+
+/*
+ * Row softmax / log-softmax over the last dimension (any c >= 1), one warp per row.
+ *   replaces torch.nn.functional.softmax call sites on the path
+ *   (models/model_3detr.py:99 objectness, :1160 weak labels; criterion.py cross-entropy)
+ */
+int coda_softmax_rows(long long rows, int c, int log_softmax, const float *x,
+                      float *y, void *stream);
+
+/*
+ * Fourier positional encoding, fused: shift/scale to the scene range, * 2 pi,
+ * 3 x d_out projection, sin | cos, channel-major store.
+ *   replaces PositionEmbeddingCoordsSine.get_fourier_embeddings
+ *   (models/position_embedding.py:89-118) + shift_scale_points (utils/pc_util.py:38-66)
+ *   xyz (b, n, 3); range_min/range_max (b, 3) or NULL when normalize == 0;
+ *   gauss_b (3, ldb) row-major, first d_out columns used; out (b, 2*d_out, n).
+ */
+int coda_fourier_pos_embed(int b, int n, int d_out, int ldb, int normalize,
+                           const float *xyz, const float *range_min,
+                           const float *range_max, const float *gauss_b,
+                           float *out, void *stream);
+
+/*
+ * Generalised 3-D IoU between predicted and ground-truth boxes, one thread per
+ * (scene, proposal, gt) triple, including the rotated-rectangle intersection
+ * (Sutherland-Hodgman clip of the two ground-plane rectangles).
+ *   replaces generalized_box3d_iou (utils/box_util.py:855-875) and what it calls:
+ *   generalized_box3d_iou_tensor (:655-757), enclosing_box3d_vol (:604-652),
+ *   box3d_vol_tensor (:581-601), polygon_clip_unnest (:540-578) -- and the
+ *   Cython copy utils/box_intersection.pyx:167-199.
+ *   corners1 (b, k1, 8, 3), corners2 (b, k2, 8, 3)  (camera frame, up = -Y),
+ *   nums_k2 (b) int32 number of real gt boxes per scene (columns >= nums_k2 -> 0),
+ *   rotated: 0 = axis-aligned intersection, 1 = polygon clip; if rotated_dev is not NULL
+ *     the flag is read from that device int instead (the reference derives it from
+ *     torch.any(gt_angles > 0).item(), criterion.py:1111 -- a host sync this avoids);
+ *   rot_k2_limit: polygon clip only for gt index < limit, others get area 0
+ *     (pass 4 to reproduce the compiled-Cython reference, whose loop bound is
+ *      rect2.shape[2] == 4, box_intersection.pyx:181; pass k2 for the intended /
+ *      TorchScript behaviour).
+ *   gious (b, k1, k2).
+ */
+int coda_giou3d(int b, int k1, int k2, int rotated, const int *rotated_dev,
+                int rot_k2_limit, const float *corners1, const float *corners2,
+                const int *nums_k2, float *gious, void *stream);
+
+/*
+ * Hungarian matching of proposals to ground truth, one CTA per scene.
+ *   replaces Matcher.forward's per-scene scipy.optimize.linear_sum_assignment
+ *   (criterion.py:59-80); cost (b, nprop, ngt) fp32 (final_cost, criterion.py:52-57),
+ *   nactual (b) int32.  Solves min sum cost[i, assign(j)] over the first nactual[b]
+ *   columns (each gt gets a distinct proposal; nprop >= nactual).
+ *   per_prop_gt_inds (b, nprop) int64 (0 where unmatched), proposal_matched_mask
+ *   (b, nprop) fp32 in {0, 1}.  Arithmetic in fp64 like scipy.
+ */
+int coda_hungarian(int b, int nprop, int ngt, const float *cost, const int *nactual,
+                   long long *per_prop_gt_inds, float *proposal_matched_mask,
+                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CODA_DETR_H */

@@ -1,0 +1,83 @@
+"""TEST-ONLY CPU stand-ins for the CUDA ops, so that the Python plumbing of the
+model / criterion can be exercised (and compared with the reference) in the
+GPU-less container.  The product package has no such path: its ops raise on CPU
+tensors.  Everything here is installed by monkeypatching from a test."""
+from __future__ import annotations
+
+import contextlib
+
+import numpy as np
+import torch
+
+import oracle_pointnet2 as orc
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def _fourier(xyz, gauss_B, d_out, input_range=None):
+    x = xyz.clone()
+    if input_range is not None:
+        x = (x - input_range[0][:, None, :]) / (input_range[1][:, None, :] - input_range[0][:, None, :])
+    x = x * (2 * np.pi)
+    proj = torch.mm(x.reshape(-1, 3), gauss_B[:, :d_out]).view(x.shape[0], x.shape[1], d_out)
+    return torch.cat([proj.sin(), proj.cos()], dim=2).permute(0, 2, 1)
+
+
+def _hungarian(cost, nactual):
+    from scipy.optimize import linear_sum_assignment
+
+    b, nprop, _ = cost.shape
+    inds = torch.zeros((b, nprop), dtype=torch.int64)
+    mask = torch.zeros((b, nprop), dtype=torch.float32)
+    c = cost.detach().cpu().numpy()
+    for i in range(b):
+        n = int(nactual[i])
+        if n > 0:
+            r, col = linear_sum_assignment(c[i, :, :n])
+            inds[i, r] = _t(col).long()
+            mask[i, r] = 1
+    return inds, mask
+
+
+@contextlib.contextmanager
+def installed(giou_fn=None, crop_fn=None):
+    """Patches coda_neurips2023_b200.{ops, pointnet2._ext} with CPU math."""
+    from coda_neurips2023_b200 import attention_sm100, ops
+    from coda_neurips2023_b200.pointnet2 import _ext
+
+    saved = {}
+
+    def patch(mod, name, fn):
+        saved[(mod, name)] = getattr(mod, name)
+        setattr(mod, name, fn)
+
+    patch(ops, "layer_norm", lambda x, w, b, eps=1e-5: torch.nn.functional.layer_norm(x, (x.shape[-1],), w, b, eps))
+    patch(ops, "softmax_rows", lambda x, log=False: (torch.log_softmax if log else torch.softmax)(x, dim=-1))
+    patch(ops, "fourier_pos_embed", _fourier)
+    patch(ops, "hungarian", _hungarian)
+    patch(ops, "attention", lambda q, k, v, nhead, dropout_p=0.0, training=False, causal=False:
+          attention_sm100._math(q, k, v, nhead, dropout_p, training, causal))
+    if giou_fn is not None:
+        patch(ops, "giou3d", giou_fn)
+    if crop_fn is not None:
+        patch(ops, "crop_resize_normalize", crop_fn)
+    patch(_ext, "furthest_point_sampling", lambda p, n: _t(orc.furthest_point_sampling(p.detach().numpy(), int(n))))
+    patch(_ext, "gather_points", lambda p, i: _t(orc.gather_points(p.detach().numpy(), i.numpy())))
+    patch(_ext, "gather_points_grad", lambda g, i, n: _t(orc.gather_points_grad(g.numpy(), i.numpy(), int(n))))
+    patch(_ext, "ball_query", lambda nx, x, r, ns: _t(orc.ball_query(nx.numpy(), x.numpy(), float(r), int(ns))))
+    patch(_ext, "group_points", lambda p, i: _t(orc.group_points(p.detach().numpy(), i.numpy())))
+    patch(_ext, "group_points_grad", lambda g, i, n: _t(orc.group_points_grad(g.numpy(), i.numpy(), int(n))))
+
+    def qg(xyz, new_xyz, radius, nsample, normalize):
+        idx, g = orc.query_and_group_xyz(xyz.numpy(), new_xyz.numpy(), float(radius), int(nsample), normalize)
+        # the CPU reference divides (torch CPU true division); keep the oracle's GPU form here
+        return _t(idx), _t(g)
+
+    patch(_ext, "query_and_group_xyz", qg)
+    try:
+        yield
+    finally:
+        for (mod, name), fn in saved.items():
+            setattr(mod, name, fn)

@@ -1,0 +1,142 @@
+"""Generates tests/golden/model_*.npz from the REFERENCE's own Python model and
+criterion, run on CPU in this container (tests/golden/_reference_harness.py):
+reference modules are imported from /root/reference, the CUDA-only pointnet2
+extension is replaced by the oracle, the absent CLIP checkpoint by a small
+random-init CLIP of the reference's own class.  Weights are filled by name
+(tests/param_fill.py), inputs come from coda_neurips2023_b200.synthetic, so only
+outputs are stored.
+
+    python tests/golden/make_model_golden.py            (writes into tests/golden/)
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parents[1]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, str(HERE))
+
+import _reference_harness as H  # noqa: E402
+from coda_neurips2023_b200 import synthetic  # noqa: E402
+from param_fill import fill_by_name  # noqa: E402
+
+CASES = {
+    # name: (batch, npoints, args overrides)
+    "stage1_small": (2, 3000, dict(nqueries=128, preenc_npoints=256, dec_dim=128, dec_nlayers=2, dec_ffn_dim=64,
+                                   enc_dropout=0.0, dec_dropout=0.0, mlp_dropout=0.0)),
+    "stage2_weak": (2, 2500, dict(nqueries=128, preenc_npoints=256, dec_dim=128, dec_nlayers=2, dec_ffn_dim=64,
+                                  enc_dropout=0.0, dec_dropout=0.0, mlp_dropout=0.0, if_clip_weak_labels=True,
+                                  loss_feat_seen_softmax_weakly_loss_with_novel_cate_confi_weight=1.0,
+                                  confidence_type="clip-max-prob")),
+}
+TINY_CLIP = dict(embed_dim=512, image_resolution=224, vision_layers=2, vision_width=128, vision_patch_size=32,
+                 context_length=77, vocab_size=49408, transformer_width=64, transformer_heads=1,
+                 transformer_layers=1)
+
+# arguments the reference reads that our make_args does not carry (weight-0 / off everywhere)
+REF_EXTRA = dict(
+    begin_keep_epoch=10 ** 14, online_nms_update_save_novel_label_clip_driven_with_cate_confidence=False,
+    save_objectness=0.75, online_nms_update_save_epoch=10, clip_driven_keep_thres=1e6, eval_layer_id=-1,
+    if_accumulate_former_pseudo_labels=False, if_with_clip=False, if_with_clip_embed=False, if_use_gt_box=False,
+    if_expand_box=False, if_with_fake_classes=False, pooling_methods="average", if_keep_box=False,
+    if_select_box_by_objectness=False, online_nms_update_novel_label=False,
+    online_nms_update_accumulate_novel_label=False, online_nms_update_accumulate_epoch=10,
+    only_image_class=False, only_prompt_loss=False, if_skip_no_seen_scene_objectness=False,
+    if_only_seen_in_loss=False, confidence_type_in_datalayer="zero-out", reset_scannet_num=0,
+)
+
+
+def reference_args(overrides):
+    from coda_neurips2023_b200.criterion import _WEIGHT_ARGS
+
+    a = synthetic.make_args(**overrides)
+    for k, v in REF_EXTRA.items():
+        if not hasattr(a, k):
+            setattr(a, k, v)
+    for attr in _WEIGHT_ARGS.values():
+        if not hasattr(a, attr):
+            setattr(a, attr, 0.0)
+    return a
+
+
+def run_reference(name):
+    batch, npoints, over = CASES[name]
+    args = reference_args(over)
+    m3 = H.load("models.model_3detr")
+    crit_mod = H.load("criterion")
+    box_util = H.load("utils.box_util")
+    clip_pkg = H.load("CLIP.clip.clip")
+    clip_model_mod = H.load("CLIP.clip.model")
+
+    class Cfg(synthetic.SyntheticDatasetConfig):  # corner builders of the REFERENCE
+        def box_parametrization_to_corners(self, c, s, a):
+            return box_util.get_3d_box_batch_tensor(s, a, box_util.flip_axis_to_camera_tensor(c))
+
+        def box_parametrization_to_corners_xyz(self, c, s, a):
+            return box_util.get_3d_box_batch_tensor_xyz(s, a, c)
+
+    cfg = Cfg(args)
+
+    def fake_clip_load(path, device="cpu", download_root=None, if_transform_tensor=True, **kw):
+        torch.manual_seed(0)
+        model = clip_model_mod.CLIP(**TINY_CLIP).float().eval()
+        fill_by_name(model, seed=11)
+        return model, clip_pkg._transform_for_tensor(model.visual.input_resolution)
+
+    clip_pkg.load = fake_clip_load
+    sys.modules["CLIP.clip"].clip.load = fake_clip_load
+    torch.manual_seed(0)
+    model, _ = m3.build_3detr_predictedbox_distillation_head(args, cfg)
+    fill_by_name(model, seed=3)
+    # re-derive the text features from the filled CLIP (they were computed in __init__)
+    with torch.no_grad():
+        model.text_features_fg = model.clip_model.encode_text(model.text).to(torch.float32)
+        model.text_features_fg_norm = model.text_features_fg / model.text_features_fg.norm(dim=1, keepdim=True)
+    criterion = crit_mod.build_criterion(args, cfg)
+    model.train()
+    model.clip_model.eval()
+    inputs = {k: torch.from_numpy(v) for k, v in synthetic.make_batch(batch, npoints, seed=5).items()}
+    np.random.seed(123)  # box selection draws (model_3detr.py:991)
+    out = model(inputs, curr_epoch=0)
+    loss, loss_dict = criterion(out, inputs)
+    loss.backward()
+    return args, model, out, loss, loss_dict
+
+
+KEEP = ("sem_cls_logits", "center_normalized", "size_normalized", "angle_logits", "angle_residual",
+        "angle_continuous", "objectness_prob", "box_corners", "box_corners_xyz")
+
+
+def main():
+    for name in CASES:
+        args, model, out, loss, loss_dict = run_reference(name)
+        last = out["outputs"]
+        blob = {f"last.{k}": last[k].detach().numpy() for k in KEEP}
+        blob["last.text_correlation_embedding"] = last["text_correlation_embedding"].detach().numpy()[:, ::4, ::8]
+        blob["last.gt_text_correlation_embedding"] = last["gt_text_correlation_embedding"].numpy()[:, :, ::8]
+        blob["last.gt_text_correlation_embedding_mask"] = last["gt_text_correlation_embedding_mask"].numpy()
+        blob["last.weak_box_cate_label"] = last["weak_box_cate_label"].numpy()
+        blob["last.weak_confidence_weight"] = last["weak_confidence_weight"].numpy()
+        blob["text_features_fg_norm"] = model.text_features_fg_norm.numpy()
+        for i, aux in enumerate(out["aux_outputs"]):
+            blob[f"aux{i}.sem_cls_logits"] = aux["sem_cls_logits"].detach().numpy()
+            blob[f"aux{i}.center_normalized"] = aux["center_normalized"].detach().numpy()
+        blob["loss"] = np.float32(loss.item())
+        for k, v in loss_dict.items():
+            blob[f"loss_dict.{k}"] = np.float32(float(v))
+        blob["state_dict_keys"] = np.array(sorted(k for k in model.state_dict().keys() if "clip_model" not in k))
+        g = dict(model.named_parameters())
+        for pname in ("pre_encoder.mlp_module.layer0.conv.weight", "encoder.layers.0.self_attn.in_proj_weight",
+                      "decoder.layers.1.multihead_attn.out_proj.weight", "mlp_heads.center_head.layers.0.weight",
+                      "decoder.norm.weight"):
+            blob[f"grad.{pname}"] = g[pname].grad.numpy()
+        np.savez_compressed(HERE / f"model_{name}.npz", **blob)
+        print("wrote", name, "loss", float(loss))
+
+
+if __name__ == "__main__":
+    main()
