@@ -16,6 +16,7 @@ LIB_PATH = _PKG / "csrc" / "libcoda_b200.so"
 INCLUDE_DIR = _PKG.parent / "include"
 
 _lib = None
+LAUNCHES = 0  # C-ABI kernel-launching calls made so far (bench.py reports the delta)
 
 
 class CodaError(RuntimeError):
@@ -51,6 +52,8 @@ def lib() -> ctypes.CDLL:
 
 
 def check(status: int, what: str) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     if status != 0:
         msg = lib().coda_status_string(int(status))
         raise CodaError(f"{what} failed: {msg.decode() if msg else status} (status {status})")

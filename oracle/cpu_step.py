@@ -1,7 +1,13 @@
-"""TEST-ONLY CPU stand-ins for the CUDA ops, so that the Python plumbing of the
-model / criterion can be exercised (and compared with the reference) in the
-GPU-less container.  The product package has no such path: its ops raise on CPU
-tensors.  Everything here is installed by monkeypatching from a test."""
+"""CPU stand-ins for the CUDA ops: the CPU restatement of the reference's training step.
+
+TEST INFRASTRUCTURE ONLY (same rule as oracle/pointnet2_oracle.c): imported by
+tests/ (plumbing parity against the reference goldens in the GPU-less container),
+by __graft_entry__.smoke() and by bench.py's `cpu_baseline` / `--impl reference`
+legs, never by the package.  With these installed, the model / criterion Python
+code runs the reference's own CPU arithmetic: torch CPU ops for everything the
+reference reaches through PyTorch, the C oracle for the pointnet2 ops (which the
+reference only has on CUDA), scipy for the assignment (criterion.py:73).
+The product package has no such path: its ops raise on CPU tensors."""
 from __future__ import annotations
 
 import contextlib
@@ -9,7 +15,11 @@ import contextlib
 import numpy as np
 import torch
 
-import oracle_pointnet2 as orc
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+import oracle_pointnet2 as orc  # noqa: E402
 
 
 def _t(a):
@@ -41,8 +51,30 @@ def _hungarian(cost, nactual):
     return inds, mask
 
 
+def _giou_cpu(c1, c2, nums_k2, rotated, rot_k2_limit=None):
+    from giou_ref import giou3d_ref
+
+    rot = bool(rotated.item()) if isinstance(rotated, torch.Tensor) else bool(rotated)
+    return giou3d_ref(c1, c2, nums_k2, rot, rot_k2_limit)
+
+
+def _crop_cpu(images, scene, boxes, valid, res, dtype=torch.float32, mean=None, std=None):
+    """The reference's own per-box op sequence (models/model_3detr.py:1034-1088) with torchvision on CPU."""
+    import ref_crop
+    from coda_neurips2023_b200.ops import CLIP_MEAN, CLIP_STD
+
+    out = torch.zeros((boxes.shape[0], 3, res, res), dtype=torch.float32)
+    m = torch.tensor(CLIP_MEAN).view(3, 1, 1)
+    s = torch.tensor(CLIP_STD).view(3, 1, 1)
+    for i in range(boxes.shape[0]):
+        if bool(valid[i]):
+            u8 = ref_crop.torchvision_sequence(images[int(scene[i])], [int(v) for v in boxes[i]], res)
+            out[i] = (u8.float() / 255.0 - m) / s
+    return out
+
+
 @contextlib.contextmanager
-def installed(giou_fn=None, crop_fn=None):
+def installed(giou_fn=_giou_cpu, crop_fn=_crop_cpu):
     """Patches coda_neurips2023_b200.{ops, pointnet2._ext} with CPU math."""
     from coda_neurips2023_b200 import attention_sm100, ops
     from coda_neurips2023_b200.pointnet2 import _ext

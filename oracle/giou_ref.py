@@ -1,8 +1,38 @@
 """torch restatement of the GIoU kernel's arithmetic (CHECKER for csrc/detr_kernels.cu
-giou3d_kernel); follows reference utils/box_util.py:655-757 with the polygon clip in
-plain Python floats -> fp32."""
+giou3d_kernel); follows reference utils/box_util.py:655-757.  The polygon clip runs in
+oracle/box_oracle.c when built (fp32), else in the Python restatement below."""
+import ctypes
+import subprocess
+from pathlib import Path
+
 import numpy as np
 import torch
+
+_HERE = Path(__file__).resolve().parent
+_BOX = None
+
+
+def _box_lib():
+    global _BOX
+    if _BOX is None:
+        so = _HERE / "liboracle_box.so"
+        if not so.exists() or so.stat().st_mtime < (_HERE / "box_oracle.c").stat().st_mtime:
+            subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
+        _BOX = ctypes.CDLL(str(so))
+    return _BOX
+
+
+def rotated_inter_areas(r1, r2, non_rot, nums_k2, k2_limit):
+    r1 = np.ascontiguousarray(r1.numpy(), np.float32)
+    r2 = np.ascontiguousarray(r2.numpy(), np.float32)
+    nr = np.ascontiguousarray(non_rot.numpy(), np.float32)
+    nk = np.ascontiguousarray(np.asarray(nums_k2), np.int32)
+    out = np.zeros_like(nr)
+    vp = ctypes.c_void_p
+    _box_lib().oracle_rotated_inter_areas(r1.shape[0], r1.shape[1], r2.shape[1], int(k2_limit),
+                                          r1.ctypes.data_as(vp), r2.ctypes.data_as(vp), nr.ctypes.data_as(vp),
+                                          nk.ctypes.data_as(vp), out.ctypes.data_as(vp))
+    return torch.from_numpy(out)
 
 
 def _inside(cp1, cp2, p):
@@ -72,12 +102,7 @@ def giou3d_ref(c1, c2, nums_k2, rotated, rot_k2_limit=None):
     inter = non_rot.clone()
     nk = [int(v) for v in nums_k2]
     if rotated:
-        inter = torch.zeros_like(non_rot)
-        for b in range(B):
-            for i in range(K1):
-                for j in range(min(nk[b], lim)):
-                    if float(non_rot[b, i, j]) != 0.0:
-                        inter[b, i, j] = _clip_area(r1[b, i].numpy(), r2[b, j].numpy())
+        inter = rotated_inter_areas(r1, r2, non_rot, nk, lim)
     inter_vol = inter * height
     union = (sum_vols - inter_vol).clamp(min=eps)
     g = (inter_vol / union - (1 - union / enclosing)) * good

@@ -7,8 +7,9 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
-if str(ROOT / "tests") not in sys.path:
-    sys.path.insert(0, str(ROOT / "tests"))
+for extra in (ROOT / "tests", ROOT / "oracle"):  # oracle/: checkers only (see its headers)
+    if str(extra) not in sys.path:
+        sys.path.insert(0, str(extra))
 
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 
