@@ -1,0 +1,296 @@
+// tcgen05 / TMA GEMM for B200:  C[b][m][n] = sum_k A[b][m][k] * B[b][n][k]  (+ bias[n]) (ReLU)
+//
+// Operands are 16-bit, K-major (K contiguous) planes; fp32 inputs are first split
+// into NSPLIT bf16 planes (x = hi + lo (+ lo2)) by the pack kernel below and the
+// GEMM accumulates the cross products hi*hi + hi*lo + lo*hi (+ ...) in fp32 in
+// TMEM, which gives fp32-class accuracy on the bf16 tensor-core path.  NSPLIT = 1
+// with fp16 operands is the CLIP ViT path.
+//
+// Structure (one CTA per 128 x BN output tile, 256 threads):
+//   warp 0 lane 0 : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem stages)
+//   warp 1 lane 0 : MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, accumulator in TMEM)
+//   warp 2        : TMEM allocator / deallocator
+//   warps 4..7    : epilogue       (tcgen05.ld 32x32b -> +bias/ReLU -> global)
+// C-ABI in include/coda_gemm.h.
+#include "../../include/coda_gemm.h"
+#include "sm100_primitives.cuh"
+
+using namespace coda;
+
+namespace {
+
+// ------------------------------------------------------------------ pack (fp32 -> bf16 planes)
+template <int NSPLIT>
+__device__ __forceinline__ void split_store(float x, __nv_bfloat16 *dst, size_t plane_stride) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  dst[0] = h;
+  if (NSPLIT >= 2) {
+    const float r1 = x - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    dst[plane_stride] = m;
+    if (NSPLIT >= 3) dst[2 * plane_stride] = __float2bfloat16_rn(r1 - __bfloat162float(m));
+  }
+}
+
+// source is row-major along k (src_k_stride == 1): one thread per (row, k) element, k fastest
+template <int NSPLIT>
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(long long rows, int k, int kpad, long long src_row_stride, const float *__restrict__ src,
+                 float scale, __nv_bfloat16 *__restrict__ planes, long long plane_stride) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * kpad) return;
+  const long long r = idx / kpad;
+  const int c = (int)(idx - r * kpad);
+  const float x = c < k ? __ldg(src + r * src_row_stride + c) * scale : 0.f;
+  split_store<NSPLIT>(x, planes + idx, (size_t)plane_stride);
+}
+
+// source is contiguous along rows (src_row_stride == 1, "transposed" operand): 32x32 smem transpose
+template <int NSPLIT>
+__global__ void __launch_bounds__(256)
+pack_transposed_kernel(long long rows, int k, int kpad, long long src_k_stride, const float *__restrict__ src,
+                       float scale, __nv_bfloat16 *__restrict__ planes, long long plane_stride) {
+  __shared__ float tile[32][33];
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i;
+    const long long r = r0 + tx;
+    tile[i][tx] = (c < k && r < rows) ? __ldg(src + (long long)c * src_k_stride + r) * scale : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const long long r = r0 + i;
+    const int c = c0 + tx;
+    if (r < rows && c < kpad) split_store<NSPLIT>(tile[tx][i], planes + r * kpad + c, (size_t)plane_stride);
+  }
+}
+
+// ------------------------------------------------------------------ GEMM
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 x 2 B = one 128-byte swizzle span
+
+struct GemmMaps {
+  CUtensorMap a[3];
+  CUtensorMap b[3];
+};
+
+// which (A plane, B plane) pairs are multiplied; small cross terms first
+__host__ __device__ constexpr int n_products(int ns) { return ns == 1 ? 1 : (ns == 2 ? 3 : 6); }
+__host__ __device__ constexpr int prod_a(int ns, int p) {
+  return ns == 1 ? 0 : ns == 2 ? (p == 0 ? 1 : 0) : (p == 0 ? 1 : p == 1 ? 2 : p == 2 ? 0 : p == 3 ? 1 : 0);
+}
+__host__ __device__ constexpr int prod_b(int ns, int p) {
+  return ns == 1 ? 0 : ns == 2 ? (p == 1 ? 1 : 0) : (p == 0 ? 1 : p == 1 ? 0 : p == 2 ? 2 : p == 3 ? 0 : p == 4 ? 1 : 0);
+}
+
+template <int NSPLIT, int BN, int STAGES, bool FP16>
+__global__ void __launch_bounds__(256, 1)
+gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, int b_batched,
+               const float *__restrict__ bias, int relu, float *__restrict__ c, long long ldc,
+               long long c_batch_stride) {
+  constexpr int A_TILE = BM * BK * 2;
+  constexpr int B_TILE = BN * BK * 2;
+  constexpr int STAGE = NSPLIT * (A_TILE + B_TILE);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, batch = blockIdx.z;
+  const int nkb = kpad / BK;
+
+  if (warp == 0 && lane == 0) {
+#pragma unroll
+    for (int p = 0; p < NSPLIT; ++p) { prefetch_tmap(&maps.a[p]); prefetch_tmap(&maps.b[p]); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    mbar_fence_init_cluster();
+  }
+  if (warp == 2) tmem_alloc(&tmem_slot, BN < 32 ? 32 : BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE);
+        unsigned char *st = smem + (size_t)s * STAGE;
+#pragma unroll
+        for (int p = 0; p < NSPLIT; ++p) {
+          tma_load_3d(st + p * A_TILE, &maps.a[p], &full_bar[s], kb * BK, m0, batch);
+          tma_load_3d(st + NSPLIT * A_TILE + p * B_TILE, &maps.b[p], &full_bar[s], kb * BK, n0,
+                      b_batched ? batch : 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_f16(FP16 ? 1 : 0, BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        unsigned char *st = smem + (size_t)s * STAGE;
+#pragma unroll
+        for (int p = 0; p < n_products(NSPLIT); ++p) {
+          const uint64_t ad = umma_smem_desc_k_sw128(st + prod_a(NSPLIT, p) * A_TILE);
+          const uint64_t bd = umma_smem_desc_k_sw128(st + NSPLIT * A_TILE + prod_b(NSPLIT, p) * B_TILE);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk)
+            umma_f16(tmem_base, umma_desc_advance(ad, kk * 32), umma_desc_advance(bd, kk * 32), idesc,
+                     (uint32_t)((kb | p | kk) != 0));
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(&tmem_full_bar);   // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp - 4;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    float *crow = c + (size_t)batch * c_batch_stride + (size_t)row * ldc;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (row < m) {
+        const int col0 = n0 + c0;
+        if (col0 + 32 <= n && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                   __uint_as_float(r[j + 3]));
+            if (bias) {
+              v.x += __ldg(bias + col0 + j); v.y += __ldg(bias + col0 + j + 1);
+              v.z += __ldg(bias + col0 + j + 2); v.w += __ldg(bias + col0 + j + 3);
+            }
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            *reinterpret_cast<float4 *>(crow + col0 + j) = v;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < n) {
+              float v = __uint_as_float(r[j]);
+              if (bias) v += __ldg(bias + col);
+              if (relu) v = fmaxf(v, 0.f);
+              crow[col] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+}
+
+template <int NSPLIT, int BN, int STAGES, bool FP16>
+int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_batched, const float *bias, int relu,
+                float *c, long long ldc, long long c_batch_stride, cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * NSPLIT * (BM * BK * 2 + BN * BK * 2) + 1024;
+  auto kern = gemm_nt_kernel<NSPLIT, BN, STAGES, FP16>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, batch);
+  kern<<<grid, 256, smem, s>>>(maps, m, n, kpad, b_batched, bias, relu, c, ldc, c_batch_stride);
+  return launch_status();
+}
+
+}  // namespace
+
+extern "C" {
+
+int coda_pack_split_bf16_strided(long long rows, int k, int kpad, long long src_row_stride,
+                                 long long src_k_stride, const float *src, float scale, int nsplit, void *planes,
+                                 long long plane_stride, void *stream) {
+  if (rows < 0 || k < 0 || kpad < k || kpad % 64 != 0 || nsplit < 1 || nsplit > 3) return CODA_EINVAL;
+  if (rows == 0 || kpad == 0) return CODA_OK;
+  if (!src || !planes) return CODA_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  __nv_bfloat16 *out = (__nv_bfloat16 *)planes;
+  if (src_k_stride == 1 || k <= 1) {
+    const long long total = rows * kpad;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (nsplit == 1) pack_rows_kernel<1><<<grid, 256, 0, s>>>(rows, k, kpad, src_row_stride, src, scale, out, plane_stride);
+    else if (nsplit == 2) pack_rows_kernel<2><<<grid, 256, 0, s>>>(rows, k, kpad, src_row_stride, src, scale, out, plane_stride);
+    else pack_rows_kernel<3><<<grid, 256, 0, s>>>(rows, k, kpad, src_row_stride, src, scale, out, plane_stride);
+  } else if (src_row_stride == 1) {
+    const dim3 grid((unsigned)((rows + 31) / 32), (kpad + 31) / 32);
+    if (grid.y > 65535) return CODA_ETOOLARGE;
+    if (nsplit == 1) pack_transposed_kernel<1><<<grid, 256, 0, s>>>(rows, k, kpad, src_k_stride, src, scale, out, plane_stride);
+    else if (nsplit == 2) pack_transposed_kernel<2><<<grid, 256, 0, s>>>(rows, k, kpad, src_k_stride, src, scale, out, plane_stride);
+    else pack_transposed_kernel<3><<<grid, 256, 0, s>>>(rows, k, kpad, src_k_stride, src, scale, out, plane_stride);
+  } else {
+    return CODA_EINVAL;  // one of the two strides must be 1
+  }
+  return launch_status();
+}
+
+int coda_pack_split_bf16(long long rows, int k, int kpad, long long src_row_stride, long long src_k_stride,
+                         const float *src, float scale, int nsplit, void *planes, void *stream) {
+  return coda_pack_split_bf16_strided(rows, k, kpad, src_row_stride, src_k_stride, src, scale, nsplit, planes,
+                                      rows * kpad, stream);
+}
+
+int coda_gemm_nt(int nsplit, int is_fp16, int batch, int m, int n, int kpad, const void *a,
+                 long long a_plane_stride, long long a_batch_stride, const void *b, long long b_plane_stride,
+                 long long b_batch_stride, const float *bias, int relu, float *c, long long ldc,
+                 long long c_batch_stride, void *stream) {
+  if (nsplit < 1 || nsplit > 3 || batch < 0 || m < 0 || n < 0 || kpad < 0 || kpad % 64 != 0) return CODA_EINVAL;
+  if (is_fp16 && nsplit != 1) return CODA_EINVAL;
+  if (batch == 0 || m == 0 || n == 0) return CODA_OK;
+  if (!a || !b || !c || kpad == 0 || batch > 65535) return CODA_EINVAL;
+  const int bn = n <= 64 ? 64 : 128;
+  GemmMaps maps;
+  const char *ap = (const char *)a, *bp = (const char *)b;
+  for (int p = 0; p < nsplit; ++p) {
+    int st = make_tmap_k_major_16b(&maps.a[p], ap + (size_t)p * a_plane_stride * 2, is_fp16, kpad, m, batch, kpad,
+                                   a_batch_stride, BM);
+    if (st != CODA_OK) return st;
+    st = make_tmap_k_major_16b(&maps.b[p], bp + (size_t)p * b_plane_stride * 2, is_fp16, kpad, n,
+                               b_batch_stride ? batch : 1, kpad, b_batch_stride, bn);
+    if (st != CODA_OK) return st;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int bb = b_batch_stride ? 1 : 0;
+#define CODA_GEMM(NS, BN_, ST, F16) \
+  return launch_gemm<NS, BN_, ST, F16>(maps, batch, m, n, kpad, bb, bias, relu, c, ldc, c_batch_stride, s)
+  if (is_fp16) {
+    if (bn == 64) CODA_GEMM(1, 64, 6, true);
+    CODA_GEMM(1, 128, 6, true);
+  }
+  if (nsplit == 1) {
+    if (bn == 64) CODA_GEMM(1, 64, 6, false);
+    CODA_GEMM(1, 128, 6, false);
+  }
+  if (nsplit == 2) {
+    if (bn == 64) CODA_GEMM(2, 64, 4, false);
+    CODA_GEMM(2, 128, 3, false);
+  }
+  if (bn == 64) CODA_GEMM(3, 64, 3, false);
+  CODA_GEMM(3, 128, 2, false);
+#undef CODA_GEMM
+}
+
+}  // extern "C"

@@ -194,3 +194,53 @@ def crop_resize_normalize(images: torch.Tensor, scene: torch.Tensor, boxes: torc
                                               stream_of(img))
     check(st, "crop_resize_normalize")
     return out
+
+
+# --------------------------------------------------------------------------- tcgen05 GEMM
+DEFAULT_NSPLIT = 2  # bf16 planes per fp32 operand: 2 -> hi*hi + hi*lo + lo*hi (~16 mantissa bits)
+
+
+def _pad64(k: int) -> int:
+    return (k + 63) // 64 * 64
+
+
+def pack_split(x: torch.Tensor, rows: int, k: int, row_stride: int, k_stride: int, nsplit: int = DEFAULT_NSPLIT,
+               scale: float = 1.0, batch: int = 1, batch_stride: int = 0) -> torch.Tensor:
+    """fp32 matrix/matrices addressed as x[b*batch_stride + r*row_stride + c*k_stride] -> bf16 planes
+    (nsplit, batch, rows, kpad), K zero-padded to a multiple of 64 (operand format of gemm_nt)."""
+    _need_cuda(x, "pack_split")
+    assert x.dtype == torch.float32
+    kpad = _pad64(k)
+    out = torch.empty((nsplit, batch, rows, kpad), dtype=torch.bfloat16, device=x.device)
+    base = x.data_ptr()
+    with torch.cuda.device(x.device):
+        for b in range(batch):
+            # planes of one batch entry are (batch * rows * kpad) apart: pack plane-by-plane views
+            st = lib().coda_pack_split_bf16_strided(
+                _ll(rows), _i(k), _i(kpad), _ll(row_stride), _ll(k_stride),
+                ctypes.c_void_p(base + 4 * b * batch_stride), _f(scale), _i(nsplit),
+                ctypes.c_void_p(out.data_ptr() + 2 * b * rows * kpad), _ll(batch * rows * kpad), stream_of(x))
+            check(st, "pack_split_bf16")
+    return out
+
+
+def gemm_nt(a_planes: torch.Tensor, b_planes: torch.Tensor, m: int, n: int, bias=None, relu: bool = False,
+            out: torch.Tensor | None = None) -> torch.Tensor:
+    """C[b] = A[b] @ B[b]^T (+ bias) from packed planes (nsplit, batch, rows, kpad); B may have batch 1
+    (shared weights).  fp16 planes (nsplit == 1) select the fp16 tensor-core path.  Returns fp32 (batch, m, n)."""
+    _need_cuda(a_planes, "gemm_nt")
+    nsplit, batch, _, kpad = a_planes.shape
+    assert b_planes.shape[0] == nsplit and b_planes.shape[3] == kpad and a_planes.dtype == b_planes.dtype
+    is_fp16 = a_planes.dtype == torch.float16
+    bb = b_planes.shape[1]
+    assert bb in (1, batch)
+    if out is None:
+        out = torch.empty((batch, m, n), dtype=torch.float32, device=a_planes.device)
+    with torch.cuda.device(a_planes.device):
+        st = lib().coda_gemm_nt(
+            _i(nsplit), _i(1 if is_fp16 else 0), _i(batch), _i(m), _i(n), _i(kpad), ptr(a_planes),
+            _ll(a_planes.stride(0)), _ll(a_planes.stride(1)), ptr(b_planes), _ll(b_planes.stride(0)),
+            _ll(b_planes.stride(1) if bb > 1 else 0), ptr(bias), _i(1 if relu else 0), ptr(out), _ll(out.stride(1)),
+            _ll(out.stride(0)), stream_of(a_planes))
+    check(st, "gemm_nt")
+    return out

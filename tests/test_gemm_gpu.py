@@ -1,0 +1,73 @@
+"""tcgen05 GEMM (include/coda_gemm.h) against a float64 matmul of the same operands."""
+import pytest
+import torch
+
+from coda_neurips2023_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib(built_lib):
+    pass
+
+
+def _ref(a, b, bias=None, relu=False):
+    c = torch.matmul(a.double(), b.double().transpose(-1, -2))
+    if bias is not None:
+        c = c + bias.double()
+    return c.relu() if relu else c
+
+
+# error of the split: products carry ~8 / 16 / 24 mantissa bits of each operand
+TOL = {1: 1.2e-2, 2: 6e-5, 3: 2e-6}
+
+
+@pytest.mark.parametrize("nsplit", [2, 1, 3])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (256, 128, 256), (300, 200, 100), (2048, 768, 256), (77, 13, 3),
+                                   (128, 64, 512), (1000, 512, 512)])
+def test_gemm_nt_vs_fp64(nsplit, m, n, k):
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k, device="cuda")
+    b = torch.randn(n, k, device="cuda")
+    bias = torch.randn(n, device="cuda")
+    ap = ops.pack_split(a, m, k, k, 1, nsplit)
+    bp = ops.pack_split(b, n, k, k, 1, nsplit)
+    c = ops.gemm_nt(ap, bp, m, n, bias=bias)[0]
+    ref = _ref(a, b, bias)
+    scale = (a.double().abs() @ b.double().abs().t()).max()  # sum |a||b|: the natural error scale
+    err = ((c.double() - ref).abs().max() / scale).item()
+    assert err < TOL[nsplit], f"nsplit={nsplit} m={m} n={n} k={k}: err {err:.2e}"
+    c2 = ops.gemm_nt(ap, bp, m, n, bias=None, relu=True)[0]
+    ref2 = _ref(a, b, None, True)
+    assert ((c2.double() - ref2).abs().max() / scale).item() < TOL[nsplit]
+
+
+def test_gemm_transposed_pack_and_batch():
+    torch.manual_seed(0)
+    x = torch.randn(4, 96, 500, device="cuda")       # (B, Cin, L): conv1d-style input
+    w = torch.randn(160, 96, device="cuda")
+    # Y_b^T (L, Cout) = X_b^T (L, Cin) @ W^T : A rows = L, k = Cin, element (l, ci) at x[b, ci, l]
+    ap = ops.pack_split(x, 500, 96, 1, 500, 2, batch=4, batch_stride=96 * 500)
+    bp = ops.pack_split(w, 160, 96, 96, 1, 2)
+    y = ops.gemm_nt(ap, bp, 500, 160)
+    ref = torch.einsum("bcl,oc->blo", x.double(), w.double())
+    scale = torch.einsum("bcl,oc->blo", x.double().abs(), w.double().abs()).max()
+    assert ((y.double() - ref).abs().max() / scale).item() < TOL[2]
+    # batched B as well (attention-style): C[b] = A[b] @ B[b]^T
+    a = torch.randn(3, 200, 64, device="cuda")
+    b = torch.randn(3, 150, 64, device="cuda")
+    ap = ops.pack_split(a, 200, 64, 64, 1, 2, batch=3, batch_stride=200 * 64)
+    bp = ops.pack_split(b, 150, 64, 64, 1, 2, batch=3, batch_stride=150 * 64)
+    c = ops.gemm_nt(ap, bp, 200, 150)
+    ref = torch.bmm(a.double(), b.double().transpose(1, 2))
+    assert ((c.double() - ref).abs().max() / 64).item() < 1e-4
+
+
+def test_gemm_fp16_operands():
+    torch.manual_seed(1)
+    a = (torch.randn(1, 1, 256, 768, device="cuda") * 0.5).half()
+    b = (torch.randn(1, 1, 3072, 768, device="cuda") * 0.05).half()
+    c = ops.gemm_nt(a, b, 256, 3072)[0]
+    ref = a[0, 0].double() @ b[0, 0].double().t()
+    assert ((c.double() - ref).abs().max() / ref.abs().max()).item() < 2e-3
