@@ -24,6 +24,20 @@ from torch import nn
 from .. import ops
 
 
+def _linear(x, w, b):
+    """fp16 activations x fp16 weights on the fp16 tcgen05 path; fp32 (CPU checks) through torch."""
+    if x.is_cuda and x.dtype == torch.float16 and x.shape[-1] % 64 == 0:
+        return ops.linear(x, w, b)
+    return F.linear(x, w, b)
+
+
+class _MLP(nn.Sequential):
+    def forward(self, x):
+        h = _linear(x, self.c_fc.weight, self.c_fc.bias)
+        h = self.gelu(h)
+        return _linear(h, self.c_proj.weight, self.c_proj.bias)
+
+
 class LayerNorm(nn.LayerNorm):
     """LayerNorm computed in fp32 whatever the activation dtype (reference :254-260)."""
 
@@ -47,9 +61,9 @@ class _PackedSelfAttention(nn.Module):
         self.out_proj = nn.Linear(d_model, d_model)
 
     def forward(self, x: torch.Tensor, causal: bool = False):
-        q, k, v = F.linear(x, self.in_proj_weight, self.in_proj_bias).split(self.embed_dim, dim=-1)
+        q, k, v = _linear(x, self.in_proj_weight, self.in_proj_bias).split(self.embed_dim, dim=-1)
         out = ops.attention(q, k, v, self.num_heads, 0.0, False, causal=causal)
-        return self.out_proj(out)
+        return _linear(out, self.out_proj.weight, self.out_proj.bias)
 
 
 class ResidualAttentionBlock(nn.Module):
@@ -57,7 +71,7 @@ class ResidualAttentionBlock(nn.Module):
         super().__init__()
         self.attn = _PackedSelfAttention(d_model, n_head)
         self.ln_1 = LayerNorm(d_model)
-        self.mlp = nn.Sequential(OrderedDict([
+        self.mlp = _MLP(OrderedDict([
             ("c_fc", nn.Linear(d_model, d_model * 4)),
             ("gelu", QuickGELU()),
             ("c_proj", nn.Linear(d_model * 4, d_model)),

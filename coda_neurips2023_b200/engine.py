@@ -20,6 +20,7 @@ import math
 import torch
 import torch.distributed as dist
 
+from . import ops
 from .utils.dist import get_world_size, is_distributed
 
 
@@ -89,4 +90,5 @@ class TrainStep:
         if self.args.clip_gradient > 0:
             torch.nn.utils.clip_grad_norm_([self.flat.flat_param], self.args.clip_gradient)
         self.optimizer.step()
+        ops.invalidate_weight_cache()  # packed bf16 weight planes are stale now
         return loss.detach(), loss_dict

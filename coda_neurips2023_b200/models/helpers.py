@@ -8,8 +8,10 @@ from __future__ import annotations
 import copy
 from functools import partial
 
+import torch
 import torch.nn as nn
 
+from .. import ops
 from ..ops import LayerNorm
 
 
@@ -85,7 +87,34 @@ class GenericMLP(nn.Module):
                 func(param)
 
     def forward(self, x):
-        return self.layers(x)
+        """(B, C, L) for the conv variant, (..., C) for the linear one.  The 1x1 convolutions are
+        GEMMs over the channel dim: run channels-last as (B*L, C) rows on ops.linear (tcgen05), with
+        BatchNorm1d / ReLU / Dropout applied to the same 2-D tensor; ReLU directly after a dense
+        layer is fused into the GEMM epilogue."""
+        conv = isinstance(self.layers[0], nn.Conv1d)
+        if conv:
+            b, c, l = x.shape
+            h = x.transpose(1, 2).reshape(b * l, c)
+        else:
+            lead = x.shape[:-1]
+            h = x.reshape(-1, x.shape[-1])
+        mods = list(self.layers)
+        i = 0
+        while i < len(mods):
+            mod = mods[i]
+            if isinstance(mod, (nn.Conv1d, nn.Linear)):
+                fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                h = ops.linear(h, mod.weight.reshape(mod.weight.shape[0], -1), mod.bias, relu=fuse)
+                i += 2 if fuse else 1
+            elif isinstance(mod, nn.GroupNorm):  # "ln" over conv channels: per-sample norm, keep the module
+                h = mod(h.view(b, l, -1).transpose(1, 2)).transpose(1, 2).reshape(b * l, -1)
+                i += 1
+            else:                                  # BatchNorm1d on (N, C), ReLU, Dropout, LayerNorm
+                h = mod(h)
+                i += 1
+        if conv:
+            return h.view(b, l, -1).transpose(1, 2)
+        return h.view(*lead, -1)
 
 
 def get_clones(module, N):

@@ -36,7 +36,7 @@ class MultiheadAttention(nn.Module):
         self.head_dim = embed_dim // num_heads
         self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
         self.in_proj_bias = nn.Parameter(torch.empty(3 * embed_dim))
-        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=True)
+        self.out_proj = ops.Linear(embed_dim, embed_dim, bias=True)
         self._reset_parameters()
 
     def _reset_parameters(self):
@@ -51,14 +51,14 @@ class MultiheadAttention(nn.Module):
         e = self.embed_dim
         w, b = self.in_proj_weight, self.in_proj_bias
         if query is key and key is value:      # encoder self-attention: one packed GEMM
-            q, k, v = nn.functional.linear(query, w, b).split(e, dim=-1)
+            q, k, v = ops.linear(query, w, b).split(e, dim=-1)
         elif query is key:                      # decoder self-attention: q = k = tgt + pos, v = tgt
-            q, k = nn.functional.linear(query, w[: 2 * e], b[: 2 * e]).split(e, dim=-1)
-            v = nn.functional.linear(value, w[2 * e:], b[2 * e:])
+            q, k = ops.linear(query, w[: 2 * e], b[: 2 * e]).split(e, dim=-1)
+            v = ops.linear(value, w[2 * e:], b[2 * e:])
         else:                                   # cross-attention
-            q = nn.functional.linear(query, w[:e], b[:e])
-            k = nn.functional.linear(key, w[e: 2 * e], b[e: 2 * e])
-            v = nn.functional.linear(value, w[2 * e:], b[2 * e:])
+            q = ops.linear(query, w[:e], b[:e])
+            k = ops.linear(key, w[e: 2 * e], b[e: 2 * e])
+            v = ops.linear(value, w[2 * e:], b[2 * e:])
         out = ops.attention(q, k, v, self.num_heads, self.dropout, self.training)
         return self.out_proj(out), None
 
@@ -106,9 +106,9 @@ class TransformerEncoderLayer(nn.Module):
         self.self_attn = MultiheadAttention(d_model, nhead, dropout=dropout_attn)
         self.use_ffn = use_ffn
         if self.use_ffn:
-            self.linear1 = nn.Linear(d_model, dim_feedforward, bias=ffn_use_bias)
+            self.linear1 = ops.Linear(d_model, dim_feedforward, bias=ffn_use_bias)
             self.dropout = nn.Dropout(dropout, inplace=False)
-            self.linear2 = nn.Linear(dim_feedforward, d_model, bias=ffn_use_bias)
+            self.linear2 = ops.Linear(dim_feedforward, d_model, bias=ffn_use_bias)
             self.norm2 = NORM_DICT[norm_name](d_model)
             self.dropout2 = nn.Dropout(dropout, inplace=False)
         self.norm1 = NORM_DICT[norm_name](d_model)
@@ -221,9 +221,9 @@ class TransformerDecoderLayer(nn.Module):
         self.dropout1 = nn.Dropout(dropout, inplace=False)
         self.dropout2 = nn.Dropout(dropout, inplace=False)
         self.dropout3 = nn.Dropout(dropout, inplace=False)
-        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear1 = ops.Linear(d_model, dim_feedforward)
         self.dropout = nn.Dropout(dropout, inplace=False)
-        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.linear2 = ops.Linear(dim_feedforward, d_model)
         self.activation = ACTIVATION_DICT[activation]()
         self.normalize_before = normalize_before
 

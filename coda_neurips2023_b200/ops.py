@@ -244,3 +244,92 @@ def gemm_nt(a_planes: torch.Tensor, b_planes: torch.Tensor, m: int, n: int, bias
             _ll(out.stride(0)), stream_of(a_planes))
     check(st, "gemm_nt")
     return out
+
+
+# --------------------------------------------------------------------------- Linear on the tcgen05 GEMM
+_WEIGHT_EPOCH = 0
+_WEIGHT_CACHE: dict = {}
+
+
+def invalidate_weight_cache() -> None:
+    """Call after parameters were updated through storage the tensors' version counters do not see
+    (the flat-buffer optimiser step of engine.TrainStep)."""
+    global _WEIGHT_EPOCH
+    _WEIGHT_EPOCH += 1
+    _WEIGHT_CACHE.clear()
+
+
+def _packed_weight(w: torch.Tensor, transposed: bool, nsplit: int) -> torch.Tensor:
+    """Planes of W (N, K) as a B operand: rows = N, k = K; or of W^T (rows = K, k = N) when transposed."""
+    key = (w.data_ptr(), tuple(w.shape), w._version, _WEIGHT_EPOCH, transposed, nsplit)
+    hit = _WEIGHT_CACHE.get(key)
+    if hit is None:
+        n, k = w.shape
+        wd = w.detach()
+        hit = pack_split(wd, k, n, 1, k, nsplit) if transposed else pack_split(wd, n, k, k, 1, nsplit)
+        if len(_WEIGHT_CACHE) > 512:
+            _WEIGHT_CACHE.clear()
+        _WEIGHT_CACHE[key] = hit
+    return hit
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu, nsplit):
+        m, k = x.shape
+        n = weight.shape[0]
+        xa = pack_split(x, m, k, x.stride(0), 1, nsplit)
+        y = gemm_nt(xa, _packed_weight(weight, False, nsplit), m, n, bias=bias, relu=relu)[0]
+        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.has_bias, ctx.relu, ctx.nsplit = bias is not None, relu, nsplit
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        nsplit = ctx.nsplit
+        dy = dy.contiguous()
+        if ctx.relu:
+            dy = dy * (y > 0).to(dy.dtype)
+        m, k = x.shape
+        n = weight.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dX (m, k) = dY (m, n) @ W (n, k): B operand = W^T planes (rows k, contraction n)
+            dx = gemm_nt(pack_split(dy, m, n, n, 1, nsplit), _packed_weight(weight, True, nsplit), m, k)[0]
+        if ctx.needs_input_grad[1]:
+            # dW (n, k) = dY^T (n, m) @ X (m, k): both operands contracted over m -> transposed packs
+            dyt = pack_split(dy, n, m, 1, n, nsplit)
+            xt = pack_split(x, k, m, 1, x.stride(0), nsplit)
+            dw = gemm_nt(dyt, xt, n, k)[0]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(dim=0)
+        return dx, dw, db, None, None
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool = False, nsplit: int | None = None):
+    """y = x @ weight^T + bias over the last dim of x, on the tcgen05 GEMM (fp32 in / out, bf16
+    split-operand accumulation); fp16 x / weight take the fp16 tensor-core path (inference only)."""
+    _need_cuda(x, "linear")
+    lead = x.shape[:-1]
+    k = x.shape[-1]
+    n = weight.shape[0]
+    x2 = x.reshape(-1, k)
+    if x2.dtype == torch.float16:
+        assert weight.dtype == torch.float16 and k % 64 == 0, "fp16 path needs fp16 weights and K % 64 == 0"
+        x2 = x2.contiguous()
+        y = gemm_nt(x2.view(1, 1, x2.shape[0], k), weight.detach().contiguous().view(1, 1, n, k), x2.shape[0], n,
+                    bias=None if bias is None else bias.float(), relu=relu)[0]
+        return y.to(torch.float16).reshape(*lead, n)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    w2 = weight.reshape(n, -1)
+    y = _Linear.apply(x2.float(), w2, bias, relu, DEFAULT_NSPLIT if nsplit is None else nsplit)
+    return y.reshape(*lead, n)
+
+
+class Linear(torch.nn.Linear):
+    """nn.Linear (same parameters / state-dict keys) running on the tcgen05 GEMM."""
+
+    def forward(self, x):
+        return linear(x, self.weight, self.bias)

@@ -9,7 +9,9 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence
 
+import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 
 class _NormWrap(nn.Sequential):
@@ -88,9 +90,45 @@ class Conv3d(_ConvBlock):
     _norm_cls = BatchNorm3d
 
 
+def _batch_norm_rows(bn: nn.modules.batchnorm._BatchNorm, h: torch.Tensor) -> torch.Tensor:
+    """BatchNorm{1,2,3}d semantics (train-mode batch statistics, running-stat update) on a
+    channels-last (rows, C) tensor."""
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    use_batch = bn.training or (bn.running_mean is None and bn.running_var is None)
+    return F.batch_norm(h, bn.running_mean if (not bn.training or bn.track_running_stats) else None,
+                        bn.running_var if (not bn.training or bn.track_running_stats) else None,
+                        bn.weight, bn.bias, use_batch, momentum, bn.eps)
+
+
 class SharedMLP(nn.Sequential):
     """Stack of 1x1 Conv2d blocks: `layer0`, `layer1`, ... (reference
-    pytorch_utils.py:8-33)."""
+    pytorch_utils.py:8-33).  Executed channels-last: the (B, C, npoint, nsample) map is
+    (B*npoint*nsample, C) rows, each block one tcgen05 GEMM + BatchNorm over rows + ReLU."""
+
+    def forward(self, x):
+        from .. import ops
+
+        if x.dim() != 4 or not x.is_cuda:
+            return super().forward(x)
+        b, c, p, s = x.shape
+        h = x.permute(0, 2, 3, 1).reshape(b * p * s, c)
+        for block in self:
+            for name, mod in block.named_children():
+                if isinstance(mod, nn.Conv2d):
+                    if mod.kernel_size != (1, 1):
+                        return super().forward(x)
+                    h = ops.linear(h, mod.weight.reshape(mod.weight.shape[0], -1), mod.bias)
+                elif isinstance(mod, _NormWrap):
+                    h = _batch_norm_rows(mod[0], h)
+                elif isinstance(mod, nn.ReLU):
+                    h = torch.relu(h)
+                else:
+                    h = mod(h)
+        return h.view(b, p, s, -1).permute(0, 3, 1, 2)
 
     def __init__(self, args: List[int], *, bn: bool = False, activation=nn.ReLU(inplace=True),
                  preact: bool = False, first: bool = False, name: str = ""):

@@ -89,6 +89,12 @@ def installed(giou_fn=_giou_cpu, crop_fn=_crop_cpu):
     patch(ops, "softmax_rows", lambda x, log=False: (torch.log_softmax if log else torch.softmax)(x, dim=-1))
     patch(ops, "fourier_pos_embed", _fourier)
     patch(ops, "hungarian", _hungarian)
+
+    def _linear(x, weight, bias=None, relu=False, nsplit=None):
+        y = torch.nn.functional.linear(x, weight.reshape(weight.shape[0], -1), bias)
+        return torch.relu(y) if relu else y
+
+    patch(ops, "linear", _linear)
     patch(ops, "attention", lambda q, k, v, nhead, dropout_p=0.0, training=False, causal=False:
           attention_sm100._math(q, k, v, nhead, dropout_p, training, causal))
     if giou_fn is not None:
