@@ -116,9 +116,8 @@ def cpu_step_rate(a, scenes: int, steps: int, threads: int):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             model, _ = build_model(args, cfg)
-        model.device = "cpu"
-        model = model.float().train()
-        model.clip_model.float().eval()
+        model = model.to_device("cpu").float().train()
+        model.clip_model.eval()
         criterion = build_criterion(args, cfg)
         opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=args.base_lr,
                                 weight_decay=args.weight_decay)

@@ -87,7 +87,7 @@ __host__ __device__ constexpr int prod_b(int ns, int p) {
 
 template <int NSPLIT, int BN, int STAGES, bool FP16>
 __global__ void __launch_bounds__(256, 1)
-gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, int b_batched,
+gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, int b_batched, int ksplit,
                const float *__restrict__ bias, int relu, float *__restrict__ c, long long ldc,
                long long c_batch_stride) {
   constexpr int A_TILE = BM * BK * 2;
@@ -101,8 +101,13 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, batch = blockIdx.z;
-  const int nkb = kpad / BK;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int batch = blockIdx.z / ksplit, ks = blockIdx.z - batch * ksplit;
+  // split-K: this CTA contracts k-blocks [kb0, kb0 + nkb) and adds its partial tile atomically
+  const int nkb_total = kpad / BK;
+  const int per = (nkb_total + ksplit - 1) / ksplit;
+  const int kb0 = ks * per;
+  const int nkb = max(0, min(per, nkb_total - kb0));
 
   if (warp == 0 && lane == 0) {
 #pragma unroll
@@ -130,8 +135,8 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
         unsigned char *st = smem + (size_t)s * STAGE;
 #pragma unroll
         for (int p = 0; p < NSPLIT; ++p) {
-          tma_load_3d(st + p * A_TILE, &maps.a[p], &full_bar[s], kb * BK, m0, batch);
-          tma_load_3d(st + NSPLIT * A_TILE + p * B_TILE, &maps.b[p], &full_bar[s], kb * BK, n0,
+          tma_load_3d(st + p * A_TILE, &maps.a[p], &full_bar[s], (kb0 + kb) * BK, m0, batch);
+          tma_load_3d(st + NSPLIT * A_TILE + p * B_TILE, &maps.b[p], &full_bar[s], (kb0 + kb) * BK, n0,
                       b_batched ? batch : 0);
         }
       }
@@ -157,14 +162,16 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
         }
         umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
       }
-      umma_commit(&tmem_full_bar);   // accumulator complete
+      if (nkb > 0) umma_commit(&tmem_full_bar);   // accumulator complete
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp - 4;
     const int row = m0 + q * 32 + lane;
+    if (nkb > 0) {
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
+    if (ks != 0) bias = nullptr;
     float *crow = c + (size_t)batch * c_batch_stride + (size_t)row * ldc;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -173,7 +180,17 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
       tmem_ld_wait();
       if (row < m) {
         const int col0 = n0 + c0;
-        if (col0 + 32 <= n && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
+        if (ksplit > 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < n) {
+              float v = __uint_as_float(r[j]);
+              if (bias) v += __ldg(bias + col);
+              atomicAdd(crow + col, v);
+            }
+          }
+        } else if (col0 + 32 <= n && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
@@ -199,6 +216,7 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
         }
       }
     }
+    }  // nkb > 0
   }
   tc_fence_before();
   __syncthreads();
@@ -208,12 +226,28 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
 template <int NSPLIT, int BN, int STAGES, bool FP16>
 int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_batched, const float *bias, int relu,
                 float *c, long long ldc, long long c_batch_stride, cudaStream_t s) {
+  // split-K when the output has few tiles but the contraction is long (weight gradients)
+  const long long tiles = (long long)((m + BM - 1) / BM) * ((n + BN - 1) / BN) * batch;
+  const int nkb_total = kpad / BK;
+  int ksplit = 1;
+  if (!relu && tiles < 148 && nkb_total >= 32) {
+    ksplit = (int)((2 * 148 + tiles - 1) / tiles);
+    if (ksplit > nkb_total / 8) ksplit = nkb_total / 8;
+    if (ksplit < 1) ksplit = 1;
+    if ((long long)batch * ksplit > 65535) ksplit = 1;
+  }
+  if (ksplit > 1) {
+    cudaError_t ez = cudaSuccess;
+    for (int bi = 0; bi < batch && ez == cudaSuccess; ++bi)
+      ez = cudaMemset2DAsync(c + (size_t)bi * c_batch_stride, (size_t)ldc * 4, 0, (size_t)n * 4, (size_t)m, s);
+    if (ez != cudaSuccess) return (int)ez;
+  }
   constexpr size_t smem = (size_t)STAGES * NSPLIT * (BM * BK * 2 + BN * BK * 2) + 1024;
   auto kern = gemm_nt_kernel<NSPLIT, BN, STAGES, FP16>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, batch);
-  kern<<<grid, 256, smem, s>>>(maps, m, n, kpad, b_batched, bias, relu, c, ldc, c_batch_stride);
+  const dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, batch * ksplit);
+  kern<<<grid, 256, smem, s>>>(maps, m, n, kpad, b_batched, ksplit, bias, relu, c, ldc, c_batch_stride);
   return launch_status();
 }
 

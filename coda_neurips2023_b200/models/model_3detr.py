@@ -237,6 +237,19 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
             self.test_text_features_fg_norm = (self.superset_text_features_fg_norm if self.if_clip_superset
                                                else self.text_features_fg_norm)
 
+    def to_device(self, device):
+        """`.to(device)` plus the plain-tensor attributes the reference keeps outside buffers
+        (text features), and the device string the CLIP branch allocates on."""
+        self.to(device)
+        self.device = str(device)
+        for name in ("text_features_fg", "text_features_fg_norm", "superset_text_features_fg_norm",
+                     "test_text_features_fg_norm"):
+            if isinstance(getattr(self, name, None), torch.Tensor):
+                setattr(self, name, getattr(self, name).to(device))
+        if str(device) == "cpu" and self.if_with_clip_train:
+            self.clip_model.float()
+        return self
+
     def build_mlp_heads(self, dataset_config, decoder_dim, mlp_dropout):
         mlp_func = partial(GenericMLP, norm_fn_name="bn1d", activation="relu", use_conv=True,
                            hidden_dims=[decoder_dim, decoder_dim], dropout=mlp_dropout, input_dim=decoder_dim)

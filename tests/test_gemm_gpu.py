@@ -71,3 +71,34 @@ def test_gemm_fp16_operands():
     c = ops.gemm_nt(a, b, 256, 3072)[0]
     ref = a[0, 0].double() @ b[0, 0].double().t()
     assert ((c.double() - ref).abs().max() / ref.abs().max()).item() < 2e-3
+
+
+def test_gemm_split_k_weight_gradient_shape():
+    """few output tiles, very long contraction (dW = dY^T X over a million rows) -> split-K path"""
+    torch.manual_seed(2)
+    m, n, k = 200000, 128, 64
+    x = torch.randn(m, k, device="cuda")
+    dy = torch.randn(m, n, device="cuda")
+    dyt = ops.pack_split(dy, n, m, 1, n, 3)
+    xt = ops.pack_split(x, k, m, 1, k, 3)
+    dw = ops.gemm_nt(dyt, xt, n, k)[0]
+    ref = dy.double().t() @ x.double()
+    assert ((dw.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+
+
+def test_linear_autograd_matches_torch():
+    torch.manual_seed(3)
+    x = torch.randn(3000, 256, device="cuda", requires_grad=True)
+    w = (torch.randn(512, 256, device="cuda") * 0.05).requires_grad_(True)
+    b = torch.randn(512, device="cuda", requires_grad=True)
+    for relu in (False, True):
+        y = ops.linear(x, w, b, relu=relu)
+        ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+        ref = ref.relu() if relu else ref
+        torch.testing.assert_close(y.double(), ref, rtol=1e-5, atol=1e-5)
+        g = torch.randn_like(y)
+        gx, gw, gb = torch.autograd.grad(y, (x, w, b), g)
+        rx, rw, rb = torch.autograd.grad(ref, (x, w, b), g.double())
+        torch.testing.assert_close(gx.double(), rx, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(gw.double(), rw, rtol=1e-5, atol=1e-4)
+        torch.testing.assert_close(gb.double(), rb, rtol=1e-5, atol=1e-4)
