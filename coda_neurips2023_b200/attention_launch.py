@@ -1,0 +1,72 @@
+"""Launcher of the tcgen05 attention forward (include/coda_attention.h) and the torch-side
+twin of its counter-based dropout mask (used by the interim autograd backward)."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import check, lib, ptr, stream_of
+
+_SEED_DEV: dict = {}   # device -> uint32 step counter living on the device
+_CALL_SALT = 0
+
+
+def seed_counter(device) -> torch.Tensor:
+    key = str(device)
+    if key not in _SEED_DEV:
+        _SEED_DEV[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _SEED_DEV[key]
+
+
+def advance_seed(device) -> None:
+    """Once per training step (captured in the step's CUDA graph): new dropout masks next step."""
+    seed_counter(device).add_(7919)
+
+
+def next_salt() -> int:
+    """Distinct per attention call site within a step (host-side, deterministic sequence)."""
+    global _CALL_SALT
+    _CALL_SALT = (_CALL_SALT * 1103515245 + 12345) & 0x7FFFFFFF
+    return _CALL_SALT
+
+
+def forward(q, k, v, nhead: int, dropout_p: float = 0.0, salt: int = 0, nsplit: int = 3):
+    """q (Lq, B, E), k / v (Lk, B, E) fp32 contiguous -> (out (Lq, B, E), lse (B*H, Lq))."""
+    lq, b, e = q.shape
+    lk = k.shape[0]
+    hd = e // nhead
+    assert hd in (64, 128), "head dim must be 64 or 128"
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    out = torch.empty_like(q)
+    lse = torch.empty((b * nhead, lq), dtype=torch.float32, device=q.device)
+    L = lib()
+    L.coda_attention_workspace_bytes.restype = ctypes.c_longlong
+    ws_bytes = L.coda_attention_workspace_bytes(b, nhead, lq, lk, hd, nsplit)
+    ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=q.device)
+    seed_dev = seed_counter(q.device) if dropout_p > 0.0 else None
+    with torch.cuda.device(q.device):
+        st = L.coda_attention_fwd(ctypes.c_int(b), ctypes.c_int(nhead), ctypes.c_int(lq), ctypes.c_int(lk),
+                                  ctypes.c_int(hd), ctypes.c_int(nsplit), ctypes.c_float(float(hd) ** -0.5), ptr(q),
+                                  ptr(k), ptr(v), ptr(out), ptr(lse), ctypes.c_float(dropout_p),
+                                  ctypes.c_uint(salt & 0xFFFFFFFF), ptr(seed_dev), ptr(ws), stream_of(q))
+    check(st, "attention_fwd")
+    return out, lse
+
+
+def dropout_keep(bh: int, lq: int, lk: int, dropout_p: float, salt: int, device) -> torch.Tensor:
+    """(bh, lq, lk) bool keep-mask, bit-identical to drop_keep() in csrc/attention_sm100.cu."""
+    M = 0xFFFFFFFF
+    seed = (seed_counter(device).to(torch.int64) & M) + (salt & M)   # stays on the device: no sync
+    ib = torch.arange(bh, device=device, dtype=torch.int64).view(bh, 1, 1)
+    iq = torch.arange(lq, device=device, dtype=torch.int64).view(1, lq, 1)
+    ik = torch.arange(lk, device=device, dtype=torch.int64).view(1, 1, lk)
+    h = (seed + ib * 0x9E3779B1 + iq * 0x85EBCA77 + ik * 0xC2B2AE3D) & M
+    h = h ^ (h >> 15)
+    h = (h * 0x2C1B3C6D) & M
+    h = h ^ (h >> 12)
+    h = (h * 0x297A2D39) & M
+    h = h ^ (h >> 15)
+    thresh = int(np.float32(dropout_p) * np.float32(16777216.0))
+    return (h & 0xFFFFFF) >= thresh

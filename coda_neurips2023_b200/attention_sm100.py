@@ -9,12 +9,15 @@ from __future__ import annotations
 
 import ctypes
 
+import numpy as np
 import torch
 
 from ._lib import check, lib, ptr, stream_of
 
 
-def _math(q, k, v, nhead, dropout_p, training, causal):
+def _math(q, k, v, nhead, dropout_p, training, causal, keep=None):
+    """softmax(q k^T / sqrt(hd)) v per head with torch bmm (cuBLAS): numerics reference in tests and
+    the recompute of the interim backward.  `keep` is an explicit (B*H, Lq, Lk) dropout keep-mask."""
     lq, b, e = q.shape
     lk = k.shape[0]
     hd = e // nhead
@@ -25,7 +28,9 @@ def _math(q, k, v, nhead, dropout_p, training, causal):
     if causal:
         s = s + torch.full((lq, lk), float("-inf"), device=s.device, dtype=s.dtype).triu_(1)
     p = torch.softmax(s, dim=-1)
-    if training and dropout_p > 0.0:
+    if keep is not None:
+        p = p * keep.to(p.dtype) * (1.0 / (1.0 - float(np.float32(dropout_p))))
+    elif training and dropout_p > 0.0:
         p = torch.nn.functional.dropout(p, dropout_p)
     return torch.bmm(p, vh).transpose(0, 1).reshape(lq, b, e)
 
@@ -36,30 +41,41 @@ def kernel_available() -> bool:
 
 class _Attention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, nhead, causal):
+    def forward(ctx, q, k, v, nhead, dropout_p, salt):
         from . import attention_launch
 
-        out = attention_launch.forward(q, k, v, nhead, causal)
+        out, lse = attention_launch.forward(q, k, v, nhead, dropout_p, salt)
         ctx.save_for_backward(q, k, v)
-        ctx.nhead, ctx.causal = nhead, causal
+        ctx.nhead, ctx.dropout_p, ctx.salt = nhead, dropout_p, salt
         return out
 
     @staticmethod
     def backward(ctx, dout):
+        # interim backward: re-derive P with cuBLAS batched GEMMs (same dropout mask, regenerated
+        # from the counter hash); the tcgen05 backward kernel replaces this
+        from . import attention_launch
+
         q, k, v = ctx.saved_tensors
+        keep = None
+        if ctx.dropout_p > 0.0:
+            keep = attention_launch.dropout_keep(q.shape[1] * ctx.nhead, q.shape[0], k.shape[0], ctx.dropout_p,
+                                                 ctx.salt, q.device)
         with torch.enable_grad():
             qq, kk, vv = (t.detach().requires_grad_(True) for t in (q, k, v))
-            out = _math(qq, kk, vv, ctx.nhead, 0.0, False, ctx.causal)
+            out = _math(qq, kk, vv, ctx.nhead, ctx.dropout_p, False, False, keep)
         dq, dk, dv = torch.autograd.grad(out, (qq, kk, vv), dout)
-        return dq, dk, dv, None, None
+        return dq, dk, dv, None, None, None
 
 
 def attention(q, k, v, nhead, dropout_p=0.0, training=False, causal=False):
     """q (Lq, B, E), k / v (Lk, B, E) -> (Lq, B, E); see ops.attention."""
     if not q.is_cuda:
         raise RuntimeError("attention: CPU not supported")
-    if training and dropout_p > 0.0 or not kernel_available():
-        # attention-probability dropout (p = 0.1 in training) is applied on the materialised
-        # probabilities until the in-kernel Philox mask lands; eval / parity runs use the kernel
+    hd = q.shape[-1] // nhead
+    if causal or q.dtype != torch.float32 or hd not in (64, 128):
+        # CLIP text tower (causal, runs once at init) and the fp16 image tower: cuBLAS path for now
         return _math(q, k, v, nhead, dropout_p, training, causal)
-    return _Attention.apply(q, k, v, nhead, causal)
+    from . import attention_launch
+
+    p = float(dropout_p) if training else 0.0
+    return _Attention.apply(q, k, v, nhead, p, attention_launch.next_salt() if p > 0.0 else 0)

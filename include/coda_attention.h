@@ -1,0 +1,41 @@
+/*
+ * coda_attention.h -- C-ABI of the fused tcgen05 multi-head attention (forward).
+ *
+ * Replaces the attention core of torch.nn.MultiheadAttention as the reference calls it
+ * in TransformerEncoderLayer / TransformerDecoderLayer (models/transformer.py:461-479,
+ * :556-580: q scaled by 1/sqrt(hd), softmax(q k^T) with dropout on the probabilities,
+ * times v; with need_weights=True the reference also materialises and head-averages
+ * the (B*H, Lq, Lk) probabilities -- a result it then discards) and in CLIP's
+ * ResidualAttentionBlock (CLIP/clip/model.py:295-316).  The in/out projections stay
+ * separate GEMMs (coda_gemm.h).
+ *
+ * q (lq, b, h*hd), k / v (lk, b, h*hd): fp32, sequence-first, contiguous (the layout the
+ * reference's modules use);  out (lq, b, h*hd) fp32;  lse (b*h, lq) fp32 log-sum-exp of
+ * the scaled scores (for the backward pass), may be NULL.
+ * hd in {64, 128}.  nsplit in {1, 2, 3}: bf16 planes per fp32 operand (see coda_gemm.h).
+ * dropout_p in [0, 1): element (bh, i, j) of the probabilities is kept iff
+ *   (mix32(seed + bh*0x9E3779B1 + i*0x85EBCA77 + j*0xC2B2AE3D) & 0xFFFFFF) >= floor(p * 2^24)
+ * with mix32(h): h ^= h>>15; h *= 0x2C1B3C6D; h ^= h>>12; h *= 0x297A2D39; h ^= h>>15
+ * (32-bit wrap-around; the effective seed is `seed` + *seed_dev when seed_dev, a device
+ * counter, is given), and scaled by 1/(1-p) -- a counter-based mask, so the backward
+ * can regenerate it without storing it.
+ * workspace: coda_attention_workspace_bytes(...) bytes of device scratch (packed operand planes).
+ */
+#ifndef CODA_ATTENTION_H
+#define CODA_ATTENTION_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+long long coda_attention_workspace_bytes(int b, int h, int lq, int lk, int hd, int nsplit);
+
+int coda_attention_fwd(int b, int h, int lq, int lk, int hd, int nsplit, float scale,
+                       const float *q, const float *k, const float *v, float *out, float *lse,
+                       float dropout_p, unsigned int seed, const unsigned int *seed_dev,
+                       void *workspace, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CODA_ATTENTION_H */
