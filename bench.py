@@ -42,8 +42,10 @@ def parse():
     p.add_argument("--batch-per-gpu", type=int, default=8)
     p.add_argument("--npoints", type=int, default=20000)
     p.add_argument("--nqueries", type=int, default=256)
-    p.add_argument("--cpu-sample-scenes", type=int, default=2)
+    p.add_argument("--cpu-sample-scenes", type=int, default=1)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
+    p.add_argument("--nsplit", type=int, default=3, help="bf16 planes per fp32 operand on the tensor-core path")
     return p.parse_args()
 
 
@@ -139,9 +141,9 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    steps = max(1, min(a.steps, 3))
-    rate, sec = cpu_step_rate(a, a.cpu_sample_scenes, steps + 1, threads)
+    threads = min(os.cpu_count() or 1, 32)
+    steps = max(1, min(a.steps, 2))
+    rate, sec = cpu_step_rate(a, a.cpu_sample_scenes, steps, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -161,7 +163,9 @@ def attention_roofline(a, device):
     """CUDA-event timing of the dominant tensor-core kernel -- the encoder self-attention forward
     (L = 2048 seeds, 4 heads x 64) -- in isolation on the step's shapes; algorithmic FLOPs =
     4 * B * H * Lq * Lk * hd per launch (QK^T + PV)."""
-    from coda_neurips2023_b200 import attention_sm100, ops
+    import ctypes
+
+    from coda_neurips2023_b200 import _lib, attention_sm100
 
     peaks = {}
     try:
@@ -173,32 +177,50 @@ def attention_roofline(a, device):
     q = torch.randn(lq, b, h * hd, device=device)
     k = torch.randn(lk, b, h * hd, device=device)
     v = torch.randn(lk, b, h * hd, device=device)
-    with torch.no_grad():
-        for _ in range(3):
-            ops.attention(q, k, v, h)
-        torch.cuda.synchronize()
-        reps = 20
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            ops.attention(q, k, v, h)
-        e1.record()
-        torch.cuda.synchronize()
+    L = _lib.lib()
+    L.coda_attention_workspace_bytes.restype = ctypes.c_longlong
+    ns = a.nsplit
+    ws = torch.empty(int(L.coda_attention_workspace_bytes(b, h, lq, lk, hd, ns)), dtype=torch.uint8, device=device)
+    out = torch.empty_like(q)
+    lse = torch.empty(b * h, lq, device=device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    _lib.check(L.coda_attention_pack(b, h, lq, lk, hd, ns, ctypes.c_float(hd ** -0.5), P(q), P(k), P(v), P(ws),
+                                     stream), "attention_pack")
+
+    def launch():
+        return L.coda_attention_fwd_packed(b, h, lq, lk, hd, ns, P(ws), P(out), P(lse), ctypes.c_float(0.0), 0,
+                                           None, stream)
+
+    for _ in range(3):
+        _lib.check(launch(), "attention_fwd_packed")
+    torch.cuda.synchronize()
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    flops = 4.0 * b * h * lq * lk * hd
+    flops = 4.0 * b * h * lq * lk * hd          # algorithmic: QK^T + PV, 2 flops per MAC
     achieved = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "encoder self-attention forward "
-            + ("(tcgen05 fused kernel)" if attention_sm100.kernel_available() else "(INTERIM: cuBLAS bmm + softmax, "
-               "tcgen05 kernel not landed yet)"),
+    nprod = {1: 1, 2: 3, 3: 6}[ns]
+    return {"bound": "tensor", "kernel": "attn_fwd_kernel<64,%d> (tcgen05 fused encoder self-attention forward, "
+            "L=2048, 4 heads x 64, batch %d)" % (ns, b),
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1590",
-            "flops_per_launch": flops, "ms_per_launch": ms, "traffic": None}
+            "flops_per_launch": flops, "ms_per_launch": ms, "traffic": None,
+            "tensor_pipe_flops_per_launch": flops * nprod,
+            "tensor_pipe_frac": achieved * nprod / peak,
+            "note": "fp32 operands are split into %d bf16 planes, the tensor pipe executes %d bf16 MMAs per "
+                    "algorithmic MMA; `achieved`/`frac` count algorithmic FLOPs only" % (ns, nprod)}
 
 
 def run_ours(a):
     import torch.distributed as dist
 
-    from coda_neurips2023_b200 import _lib, synthetic
+    from coda_neurips2023_b200 import _lib, ops, synthetic
     from coda_neurips2023_b200.criterion import build_criterion
     from coda_neurips2023_b200.engine import TrainStep
     from coda_neurips2023_b200.models import build_model
@@ -223,6 +245,7 @@ def run_ours(a):
         model, _ = build_model(args, cfg)
     model = model.to(device).train()
     criterion = build_criterion(args, cfg).to(device)
+    ops.DEFAULT_NSPLIT = a.nsplit
     step = TrainStep(args, model, criterion, device)
     np.random.seed(1000 + rank)
 
@@ -233,6 +256,9 @@ def run_ours(a):
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0].values())
     resident = [step.to_device(h) for h in host]
     torch.cuda.synchronize()
+    use_graph = not a.no_graph
+    if use_graph:
+        step.capture(resident[0])
 
     def barrier():
         if world > 1:
@@ -260,17 +286,18 @@ def run_ours(a):
         loss, _ = step(resident[i % nb], 0.0)
     e1.record()
     barrier()
-    launches = _lib.LAUNCHES - launches0
+    launches = (_lib.LAUNCHES - launches0) if not use_graph else step.launches_per_step * a.steps
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     assert torch.isfinite(loss).item(), "non-finite loss"
     # ---------------- end-to-end leg (host buffers, H2D + loss read-back inside) ----------------
+    feed = (lambda hb: hb) if use_graph else step.to_device  # graph mode: H2D straight into the static buffers
     for i in range(min(a.warmup, 2)):
-        step(step.to_device(host[i % nb]), 0.0)
+        step(feed(host[i % nb]), 0.0)
     barrier()
     e0.record()
     d2h = 0
     for i in range(a.steps):
-        loss, _ = step(step.to_device(host[i % nb]), 0.0)
+        loss, _ = step(feed(host[i % nb]), 0.0)
         lv = loss.item()  # device -> host read of the step's result, every step
         d2h = 4
     e1.record()
@@ -291,16 +318,16 @@ def run_ours(a):
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": launches, "gpu_launches_note": "C-ABI kernel-launching calls into libcoda_b200.so inside the "
                                                         "timed region (cuBLAS/cuDNN launches of torch not counted)",
-        "clocks": clocks, "final_loss": lv,
+        "clocks": clocks, "final_loss": lv, "cuda_graph": use_graph, "operand_split": a.nsplit,
         "grad_allreduce_bytes": step.flat.nbytes(),
     }
     line["roofline"] = attention_roofline(a, device)
     if world == 1 and not a.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        rate, sec = cpu_step_rate(a, a.cpu_sample_scenes, 2, threads)
+        threads = min(os.cpu_count() or 1, 32)  # more threads only slow these small CPU ops down
+        rate, sec = cpu_step_rate(a, 1, 1, threads)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{a.cpu_sample_scenes} scenes/step, median of 2 steps ({sec:.1f} s/step): "
-                                          "reference PyTorch CPU arithmetic + C restatement of its CUDA-only ops"}
+                                "sample": f"1 scene, 1 full step ({sec:.1f} s): reference PyTorch CPU arithmetic + "
+                                          "C restatement of its CUDA-only ops; use --impl reference for more steps"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -336,35 +336,51 @@ long long coda_attention_workspace_bytes(int b, int h, int lq, int lk, int hd, i
   return 2LL * nsplit * b * h * ((long long)lq * hd + (long long)lk * hd + hd * lkpad) + 1024;
 }
 
-int coda_attention_fwd(int b, int h, int lq, int lk, int hd, int nsplit, float scale, const float *q,
-                       const float *k, const float *v, float *out, float *lse, float dropout_p,
-                       unsigned int seed, const unsigned int *seed_dev, void *workspace, void *stream) {
+static int attn_check(int b, int h, int lq, int lk, int hd, int nsplit) {
   if (b < 0 || h <= 0 || lq < 0 || lk <= 0 || (hd != 64 && hd != 128) || nsplit < 1 || nsplit > 3) return CODA_EINVAL;
+  if ((long long)b * h > 65535) return CODA_EINVAL;
+  return CODA_OK;
+}
+
+int coda_attention_pack(int b, int h, int lq, int lk, int hd, int nsplit, float scale, const float *q,
+                        const float *k, const float *v, void *workspace, void *stream) {
+  int st = attn_check(b, h, lq, lk, hd, nsplit);
+  if (st != CODA_OK) return st;
   if (b == 0 || lq == 0) return CODA_OK;
-  if (!q || !k || !v || !out || !workspace || b * h > 65535 || dropout_p < 0.f || dropout_p >= 1.f) return CODA_EINVAL;
+  if (!q || !k || !v || !workspace) return CODA_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   const int bh = b * h;
   const int lkpad = (lk + 63) / 64 * 64;
   __nv_bfloat16 *qp = (__nv_bfloat16 *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   __nv_bfloat16 *kp = qp + (size_t)nsplit * bh * lq * hd;
   __nv_bfloat16 *vp = kp + (size_t)nsplit * bh * lk * hd;
-  {
-    const long long tq = (long long)lq * bh * hd, tk = (long long)lk * bh * hd;
-    const dim3 gv((lk + 31) / 32, (hd + 31) / 32, bh);
-    const dim3 gvp((lkpad + 31) / 32, (hd + 31) / 32, bh);
+  const long long tq = (long long)lq * bh * hd, tk = (long long)lk * bh * hd;
+  const dim3 gvp((lkpad + 31) / 32, (hd + 31) / 32, bh);
 #define CODA_PACK(NS)                                                                                          \
   attn_pack_rows_kernel<NS><<<(unsigned)((tq + 255) / 256), 256, 0, s>>>(lq, b, h, hd, scale, q, qp);           \
   attn_pack_rows_kernel<NS><<<(unsigned)((tk + 255) / 256), 256, 0, s>>>(lk, b, h, hd, 1.0f, k, kp);            \
   attn_pack_vt_kernel<NS><<<gvp, 256, 0, s>>>(lk, lkpad, b, h, hd, v, vp);
-    if (nsplit == 1) { CODA_PACK(1) } else if (nsplit == 2) { CODA_PACK(2) } else { CODA_PACK(3) }
+  if (nsplit == 1) { CODA_PACK(1) } else if (nsplit == 2) { CODA_PACK(2) } else { CODA_PACK(3) }
 #undef CODA_PACK
-    (void)gv;
-    int st = launch_status();
-    if (st != CODA_OK) return st;
-  }
+  return launch_status();
+}
+
+int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, const void *workspace,
+                              float *out, float *lse, float dropout_p, unsigned int seed,
+                              const unsigned int *seed_dev, void *stream) {
+  int st = attn_check(b, h, lq, lk, hd, nsplit);
+  if (st != CODA_OK) return st;
+  if (b == 0 || lq == 0) return CODA_OK;
+  if (!out || !workspace || dropout_p < 0.f || dropout_p >= 1.f) return CODA_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int bh = b * h;
+  const int lkpad = (lk + 63) / 64 * 64;
+  const __nv_bfloat16 *qp = (const __nv_bfloat16 *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  const __nv_bfloat16 *kp = qp + (size_t)nsplit * bh * lq * hd;
+  const __nv_bfloat16 *vp = kp + (size_t)nsplit * bh * lk * hd;
   AttnMaps maps;
   for (int p = 0; p < nsplit; ++p) {
-    int st = make_tmap_k_major_16b(&maps.q[p], qp + (size_t)p * bh * lq * hd, 0, hd, lq, bh, hd, (long long)lq * hd, QT);
+    st = make_tmap_k_major_16b(&maps.q[p], qp + (size_t)p * bh * lq * hd, 0, hd, lq, bh, hd, (long long)lq * hd, QT);
     if (st != CODA_OK) return st;
     st = make_tmap_k_major_16b(&maps.k[p], kp + (size_t)p * bh * lk * hd, 0, hd, lk, bh, hd, (long long)lk * hd, KT);
     if (st != CODA_OK) return st;
@@ -382,6 +398,14 @@ int coda_attention_fwd(int b, int h, int lq, int lk, int hd, int nsplit, float s
   if (nsplit == 2) CODA_ATTN(128, 2);
   CODA_ATTN(128, 3);
 #undef CODA_ATTN
+}
+
+int coda_attention_fwd(int b, int h, int lq, int lk, int hd, int nsplit, float scale, const float *q,
+                       const float *k, const float *v, float *out, float *lse, float dropout_p,
+                       unsigned int seed, const unsigned int *seed_dev, void *workspace, void *stream) {
+  int st = coda_attention_pack(b, h, lq, lk, hd, nsplit, scale, q, k, v, workspace, stream);
+  if (st != CODA_OK) return st;
+  return coda_attention_fwd_packed(b, h, lq, lk, hd, nsplit, workspace, out, lse, dropout_p, seed, seed_dev, stream);
 }
 
 }  // extern "C"

@@ -152,6 +152,7 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
         self.if_clip_more_prompts = if_clip_more_prompts
         self.if_with_clip_train = if_with_clip_train
         self.box_idx_list = np.arange(128, dtype=np.int8)  # reference :191 (fixed, whatever nqueries is)
+        self.external_selection = None  # device (B, 32) int64 tensor when the step is CUDA-graph captured
         self.if_keep_box = if_keep_box
         self.if_select_box_by_objectness = if_select_box_by_objectness
         self.if_use_gt_box, self.if_expand_box = if_use_gt_box, if_expand_box
@@ -348,15 +349,21 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
         return {"outputs": outputs[-1], "aux_outputs": outputs[:-1]}
 
     # ------------------------------------------------------------------ CLIP crops
+    def draw_box_selection(self, bsz: int) -> np.ndarray:
+        """(bsz, distillation_box_num) int64: one `np.random.choice(arange(128), 32, replace=False)`
+        per scene, the reference's draw sequence (:991)."""
+        return np.stack([np.random.choice(self.box_idx_list, self.distillation_box_num, replace=False)
+                         for _ in range(bsz)]).astype(np.int64)
+
     def _select_boxes(self, objectness_prob, curr_epoch):
         """(B, distillation_box_num) box indices per scene.  Stage 1 (and < epoch 540):
         `np.random.choice(arange(128), 32, replace=False)` per scene on the host RNG,
         exactly the reference's draw sequence (:991)."""
         bsz = objectness_prob.shape[0]
         if (not self.if_select_box_by_objectness) or curr_epoch < 540:
-            sel = np.stack([np.random.choice(self.box_idx_list, self.distillation_box_num, replace=False)
-                            for _ in range(bsz)]).astype(np.int64)
-            return torch.from_numpy(sel).to(objectness_prob.device, non_blocking=True)
+            if self.external_selection is not None:   # drawn ahead of the (graph-captured) step
+                return self.external_selection
+            return torch.from_numpy(self.draw_box_selection(bsz)).to(objectness_prob.device, non_blocking=True)
         raise NotImplementedError("objectness-driven crop selection after epoch 540 (reference :993-1006) yields a "
                                   "variable number of crops per scene; not on the B200 path yet")
 

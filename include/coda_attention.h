@@ -35,6 +35,15 @@ int coda_attention_fwd(int b, int h, int lq, int lk, int hd, int nsplit, float s
                        float dropout_p, unsigned int seed, const unsigned int *seed_dev,
                        void *workspace, void *stream);
 
+/* The two halves of coda_attention_fwd, separately: operand packing (fp32 -> scaled, split bf16
+ * planes in `workspace`) and the fused kernel on already-packed operands (what the roofline
+ * measurement times). */
+int coda_attention_pack(int b, int h, int lq, int lk, int hd, int nsplit, float scale, const float *q,
+                        const float *k, const float *v, void *workspace, void *stream);
+int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, const void *workspace,
+                              float *out, float *lse, float dropout_p, unsigned int seed,
+                              const unsigned int *seed_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
