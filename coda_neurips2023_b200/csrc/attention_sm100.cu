@@ -320,8 +320,12 @@ int launch_attn(const AttnMaps &maps, int Lq, int Lk, int B, int H, float *out, 
                 uint32_t seed, const uint32_t *seed_dev, cudaStream_t s) {
   constexpr size_t smem = AttnSmem<HD, NSPLIT>::TOTAL + 1024;
   auto kern = attn_fwd_kernel<HD, NSPLIT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  static bool configured = false;  // once per template instance
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
   const dim3 grid((Lq + QT - 1) / QT, B * H);
   kern<<<grid, 256, smem, s>>>(maps, Lq, Lk, B, H, out, lse, drop_p, seed, seed_dev);
   return launch_status();

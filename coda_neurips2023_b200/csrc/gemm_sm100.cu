@@ -244,8 +244,12 @@ int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_b
   }
   constexpr size_t smem = (size_t)STAGES * NSPLIT * (BM * BK * 2 + BN * BK * 2) + 1024;
   auto kern = gemm_nt_kernel<NSPLIT, BN, STAGES, FP16>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  static bool configured = false;  // once per template instance
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
   const dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, batch * ksplit);
   kern<<<grid, 256, smem, s>>>(maps, m, n, kpad, b_batched, ksplit, bias, relu, c, ldc, c_batch_stride);
   return launch_status();

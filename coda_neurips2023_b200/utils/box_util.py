@@ -25,8 +25,16 @@ def flip_axis_to_camera_tensor(pc: torch.Tensor) -> torch.Tensor:
     return torch.stack((pc[..., 0], -pc[..., 2], pc[..., 1]), dim=-1)
 
 
+_SIGN_CACHE: dict = {}
+
+
 def _signs(t, like):
-    return torch.tensor(t, dtype=like.dtype, device=like.device)
+    """Corner sign pattern as a tensor on `like`'s device, built once per (pattern, device, dtype):
+    a host->device copy per call would also be illegal inside a CUDA-graph capture."""
+    key = (t, like.device, like.dtype)
+    if key not in _SIGN_CACHE:
+        _SIGN_CACHE[key] = torch.tensor(t, dtype=like.dtype, device=like.device)
+    return _SIGN_CACHE[key]
 
 
 def get_3d_box_batch_tensor(box_size, angle, center):
