@@ -70,3 +70,15 @@ def dropout_keep(bh: int, lq: int, lk: int, dropout_p: float, salt: int, device)
     h = h ^ (h >> 15)
     thresh = int(np.float32(dropout_p) * np.float32(16777216.0))
     return (h & 0xFFFFFF) >= thresh
+
+
+def dropout_mult(bh: int, lq: int, lk: int, dropout_p: float, salt: int, device) -> torch.Tensor:
+    """(bh, lq, lk) fp32 factor in {0, 1/(1-p)}: the dropout the forward kernel applied (one kernel)."""
+    out = torch.empty((bh, lq, lk), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        st = lib().coda_attention_dropout_mult(ctypes.c_int(bh), ctypes.c_int(lq), ctypes.c_int(lk),
+                                               ctypes.c_float(dropout_p), ctypes.c_uint(salt & 0xFFFFFFFF),
+                                               ptr(seed_counter(device)), ptr(out),
+                                               ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+    check(st, "attention_dropout_mult")
+    return out

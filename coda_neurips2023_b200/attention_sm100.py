@@ -29,7 +29,7 @@ def _math(q, k, v, nhead, dropout_p, training, causal, keep=None):
         s = s + torch.full((lq, lk), float("-inf"), device=s.device, dtype=s.dtype).triu_(1)
     p = torch.softmax(s, dim=-1)
     if keep is not None:
-        p = p * keep.to(p.dtype) * (1.0 / (1.0 - float(np.float32(dropout_p))))
+        p = p * (keep if keep.dtype == p.dtype else keep.to(p.dtype) * (1.0 / (1.0 - float(np.float32(dropout_p)))))
     elif training and dropout_p > 0.0:
         p = torch.nn.functional.dropout(p, dropout_p)
     return torch.bmm(p, vh).transpose(0, 1).reshape(lq, b, e)
@@ -58,7 +58,7 @@ class _Attention(torch.autograd.Function):
         q, k, v = ctx.saved_tensors
         keep = None
         if ctx.dropout_p > 0.0:
-            keep = attention_launch.dropout_keep(q.shape[1] * ctx.nhead, q.shape[0], k.shape[0], ctx.dropout_p,
+            keep = attention_launch.dropout_mult(q.shape[1] * ctx.nhead, q.shape[0], k.shape[0], ctx.dropout_p,
                                                  ctx.salt, q.device)
         with torch.enable_grad():
             qq, kk, vv = (t.detach().requires_grad_(True) for t in (q, k, v))

@@ -98,6 +98,19 @@ __device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t bh, uint32_t q
   return (h & 0xFFFFFFu) >= thresh24;
 }
 
+// materialised keep-mask * 1/(1-p) for the interim (cuBLAS) backward: mult[bh][q][k] in {0, 1/(1-p)}
+__global__ void __launch_bounds__(256)
+dropout_mult_kernel(long long total, int lq, int lk, uint32_t seed, const uint32_t *__restrict__ seed_dev,
+                    uint32_t thresh24, float keep_scale, float *__restrict__ mult) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (seed_dev) seed += __ldg(seed_dev);
+  const uint32_t k = (uint32_t)(i % lk);
+  const long long t = i / lk;
+  const uint32_t q = (uint32_t)(t % lq), bh = (uint32_t)(t / lq);
+  mult[i] = drop_keep(seed, bh, q, k, thresh24) ? keep_scale : 0.f;
+}
+
 // ------------------------------------------------------------------ the kernel
 struct AttnMaps {
   CUtensorMap q[3], k[3], v[3];
@@ -402,6 +415,17 @@ int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, 
   if (nsplit == 2) CODA_ATTN(128, 2);
   CODA_ATTN(128, 3);
 #undef CODA_ATTN
+}
+
+int coda_attention_dropout_mult(int bh, int lq, int lk, float dropout_p, unsigned int seed,
+                                const unsigned int *seed_dev, float *mult, void *stream) {
+  if (bh < 0 || lq < 0 || lk < 0 || dropout_p < 0.f || dropout_p >= 1.f) return CODA_EINVAL;
+  const long long total = (long long)bh * lq * lk;
+  if (total == 0) return CODA_OK;
+  if (!mult) return CODA_EINVAL;
+  dropout_mult_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      total, lq, lk, seed, seed_dev, (uint32_t)(dropout_p * 16777216.0f), 1.0f / (1.0f - dropout_p), mult);
+  return launch_status();
 }
 
 int coda_attention_fwd(int b, int h, int lq, int lk, int hd, int nsplit, float scale, const float *q,

@@ -44,6 +44,11 @@ int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, 
                               float *out, float *lse, float dropout_p, unsigned int seed,
                               const unsigned int *seed_dev, void *stream);
 
+/* mult[bh][q][k] = keep(bh, q, k) ? 1/(1-p) : 0 -- the dropout factor the forward kernel applied,
+ * regenerated from the counter hash (for a backward pass that materialises the probabilities). */
+int coda_attention_dropout_mult(int bh, int lq, int lk, float dropout_p, unsigned int seed,
+                                const unsigned int *seed_dev, float *mult, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

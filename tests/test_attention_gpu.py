@@ -48,6 +48,8 @@ def test_attention_dropout_mask_matches_torch_twin():
     out, _ = attention_launch.forward(q, k, v, h, dropout_p=0.1, salt=777)
     keep = attention_launch.dropout_keep(b * h, lq, lk, 0.1, 777, q.device)
     assert 0.88 < keep.float().mean().item() < 0.92
+    mult = attention_launch.dropout_mult(b * h, lq, lk, 0.1, 777, q.device)
+    assert torch.equal(mult > 0, keep) and abs(mult.max().item() - 1 / 0.9) < 1e-6
     ref = _ref64(q, k, v, h, keep, 0.1)
     assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 5e-6
 
