@@ -35,6 +35,14 @@ def adjust_learning_rate(args, optimizer, curr_epoch: float) -> float:
     return lr
 
 
+def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
+    """The step's single gradient collective: sum over ranks (NCCL over NVLink on GPUs), then /world."""
+    if is_distributed() and get_world_size() > 1:
+        dist.all_reduce(flat)
+        flat.div_(get_world_size())
+    return flat
+
+
 class FlatParameters:
     """Re-homes every trainable parameter of `module` (and its gradient) into one
     contiguous fp32 buffer each."""
@@ -157,9 +165,7 @@ class TrainStep:
         outputs = self.model(batch, curr_epoch=int(curr_epoch))
         loss, loss_dict = self.criterion(outputs, batch)
         loss.backward()
-        if self.world > 1:
-            dist.all_reduce(self.flat.flat_grad)          # the single gradient collective
-            self.flat.flat_grad.div_(self.world)
+        allreduce_mean_(self.flat.flat_grad)          # the single gradient collective
         if self.args.clip_gradient > 0:
             torch.nn.utils.clip_grad_norm_([self.flat.flat_param], self.args.clip_gradient)
         self.optimizer.step()
