@@ -257,8 +257,13 @@ def run_ours(a):
     resident = [step.to_device(h) for h in host]
     torch.cuda.synchronize()
     use_graph = not a.no_graph
+    graph_note = None
     if use_graph:
-        step.capture(resident[0])
+        try:
+            step.capture(resident[0])
+        except Exception as e:  # noqa: BLE001  (report, run eagerly: the number is still valid, just launch-bound)
+            use_graph, step.graph = False, None
+            graph_note = f"capture failed: {type(e).__name__}: {str(e)[:160]}"
 
     def barrier():
         if world > 1:
@@ -304,6 +309,13 @@ def run_ours(a):
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
+    # data-parallel sanity: after the same number of all-reduced steps every rank holds the same weights
+    param_spread = 0.0
+    if world > 1:
+        hi, lo = step.flat.flat_param.detach().clone(), step.flat.flat_param.detach().clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        param_spread = float((hi - lo).abs().max().item())
 
     if rank != 0:
         if world > 1:
@@ -318,7 +330,8 @@ def run_ours(a):
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": launches, "gpu_launches_note": "C-ABI kernel-launching calls into libcoda_b200.so inside the "
                                                         "timed region (cuBLAS/cuDNN launches of torch not counted)",
-        "clocks": clocks, "final_loss": lv, "cuda_graph": use_graph, "operand_split": a.nsplit,
+        "clocks": clocks, "final_loss": lv, "cuda_graph": use_graph, "cuda_graph_note": graph_note,
+        "operand_split": a.nsplit, "param_spread_across_ranks": param_spread,
         "grad_allreduce_bytes": step.flat.nbytes(),
     }
     line["roofline"] = attention_roofline(a, device)
