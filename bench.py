@@ -318,8 +318,7 @@ def run_ours(a):
         param_spread = float((hi - lo).abs().max().item())
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, device)
         return
     scenes = a.batch_per_gpu * world * a.steps
     line = {
@@ -342,8 +341,17 @@ def run_ours(a):
                                 "sample": f"1 scene, 1 full step ({sec:.1f} s): reference PyTorch CPU arithmetic + "
                                           "C restatement of its CUDA-only ops; use --impl reference for more steps"}
     print(json.dumps(line), flush=True)
+    _finish(world, device)
+
+
+def _finish(world, device):
+    """Leave without tearing NCCL down: destroying a communicator that a live CUDA graph still
+    references can hang at interpreter exit; every rank is done with collectives here."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize(device)
+        os._exit(0)
 
 
 def main():
