@@ -82,3 +82,24 @@ def dropout_mult(bh: int, lq: int, lk: int, dropout_p: float, salt: int, device)
                                                ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
     check(st, "attention_dropout_mult")
     return out
+
+
+def backward(q, k, v, out, dout, lse, nhead: int, dropout_p: float = 0.0, salt: int = 0):
+    """Fused tcgen05 backward (head dim 64): returns (dq, dk, dv), each shaped like its input."""
+    lq, b, e = q.shape
+    lk = k.shape[0]
+    hd = e // nhead
+    assert hd == 64
+    q, k, v, out, dout = (t.contiguous() for t in (q, k, v, out, dout))
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    L = lib()
+    L.coda_attention_bwd_workspace_bytes.restype = ctypes.c_longlong
+    ws = torch.empty(int(L.coda_attention_bwd_workspace_bytes(b, nhead, lq, lk)), dtype=torch.uint8, device=q.device)
+    seed_dev = seed_counter(q.device) if dropout_p > 0.0 else None
+    with torch.cuda.device(q.device):
+        st = L.coda_attention_bwd(ctypes.c_int(b), ctypes.c_int(nhead), ctypes.c_int(lq), ctypes.c_int(lk),
+                                  ctypes.c_int(hd), ctypes.c_float(float(hd) ** -0.5), ptr(q), ptr(k), ptr(v), ptr(out),
+                                  ptr(dout), ptr(lse), ptr(dq), ptr(dk), ptr(dv), ctypes.c_float(dropout_p),
+                                  ctypes.c_uint(salt & 0xFFFFFFFF), ptr(seed_dev), ptr(ws), stream_of(q))
+    check(st, "attention_bwd")
+    return dq, dk, dv

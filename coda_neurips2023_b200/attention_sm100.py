@@ -45,17 +45,20 @@ class _Attention(torch.autograd.Function):
         from . import attention_launch
 
         out, lse = attention_launch.forward(q, k, v, nhead, dropout_p, salt)
-        ctx.save_for_backward(q, k, v)
+        ctx.save_for_backward(q, k, v, out, lse)
         ctx.nhead, ctx.dropout_p, ctx.salt = nhead, dropout_p, salt
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        # interim backward: re-derive P with cuBLAS batched GEMMs (same dropout mask, regenerated
-        # from the counter hash); the tcgen05 backward kernel replaces this
         from . import attention_launch
 
-        q, k, v = ctx.saved_tensors
+        q, k, v, out, lse = ctx.saved_tensors
+        if q.shape[-1] // ctx.nhead == 64:
+            # encoder head size: fused tcgen05 backward (dQ kernel + dK/dV kernel)
+            dq, dk, dv = attention_launch.backward(q, k, v, out, dout, lse, ctx.nhead, ctx.dropout_p, ctx.salt)
+            return dq, dk, dv, None, None, None
+        # head dim 128 (decoder, small Lq): re-derive P with cuBLAS batched GEMMs, same dropout mask
         keep = None
         if ctx.dropout_p > 0.0:
             keep = attention_launch.dropout_mult(q.shape[1] * ctx.nhead, q.shape[0], k.shape[0], ctx.dropout_p,

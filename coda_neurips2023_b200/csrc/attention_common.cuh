@@ -1,0 +1,51 @@
+// Shared pieces of the tcgen05 attention kernels (forward: attention_sm100.cu, backward:
+// attention_bwd_sm100.cu): tile sizes, split-product tables, bf16 plane splitting, dropout hash.
+#pragma once
+#include <math.h>
+
+#include "sm100_primitives.cuh"
+
+namespace coda {
+namespace attn {
+
+constexpr int QT = 128;   // queries per CTA
+constexpr int KT = 64;    // keys per tile (one 128-byte swizzle span of bf16)
+constexpr float LOG2E = 1.4426950408889634f;
+
+__host__ __device__ constexpr int a_nprod(int ns) { return ns == 1 ? 1 : (ns == 2 ? 3 : 6); }
+__host__ __device__ constexpr int a_pa(int ns, int p) {
+  return ns == 1 ? 0 : ns == 2 ? (p == 0 ? 1 : 0) : (p == 0 ? 1 : p == 1 ? 2 : p == 2 ? 0 : p == 3 ? 1 : 0);
+}
+__host__ __device__ constexpr int a_pb(int ns, int p) {
+  return ns == 1 ? 0 : ns == 2 ? (p == 1 ? 1 : 0) : (p == 0 ? 1 : p == 1 ? 0 : p == 2 ? 2 : p == 3 ? 0 : p == 4 ? 1 : 0);
+}
+
+// ------------------------------------------------------------------ operand packing
+// src (L, B, H*HD) fp32 sequence-first.  mode 0: planes [ns][B*H][L][HD]   (q, k; K-major rows)
+//                                        mode 1: planes [ns][B*H][HD][Lpad] (v^T; keys contiguous)
+template <int NSPLIT>
+__device__ __forceinline__ void split3(float x, __nv_bfloat16 *dst, size_t plane_stride) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  dst[0] = h;
+  if (NSPLIT >= 2) {
+    const float r1 = x - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    dst[plane_stride] = m;
+    if (NSPLIT >= 3) dst[2 * plane_stride] = __float2bfloat16_rn(r1 - __bfloat162float(m));
+  }
+}
+
+// ------------------------------------------------------------------ dropout mask (counter hash)
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
+}
+// keep-decision of element (bh, q, k); identical formula in attention_launch.py for the backward
+__device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t bh, uint32_t q, uint32_t k, uint32_t thresh24) {
+  const uint32_t h = mix32(seed + bh * 0x9E3779B1u + q * 0x85EBCA77u + k * 0xC2B2AE3Du);
+  return (h & 0xFFFFFFu) >= thresh24;
+}
+
+
+}  // namespace attn
+}  // namespace coda

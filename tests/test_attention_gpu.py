@@ -69,3 +69,24 @@ def test_attention_autograd_wrapper():
     # training-mode dropout goes through the kernel + regenerated mask and stays unbiased
     outs = torch.stack([attention_sm100.attention(q, k, v, h, 0.1, True).detach() for _ in range(8)])
     assert (outs.mean(0) - ref.detach()).abs().mean().item() < 0.05
+
+
+@pytest.mark.parametrize("lq,lk,b,h", [(128, 128, 1, 1), (2048, 2048, 1, 4), (300, 200, 2, 2), (64, 1000, 2, 4), (50, 50, 3, 12)])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_attention_backward_hd64_vs_fp64(lq, lk, b, h, p):
+    torch.manual_seed(lq + lk)
+    e = h * 64
+    q = (torch.randn(lq, b, e, device="cuda") * 1.2).requires_grad_(True)
+    k = (torch.randn(lk, b, e, device="cuda") * 1.2).requires_grad_(True)
+    v = torch.randn(lk, b, e, device="cuda", requires_grad=True)
+    attention_launch.seed_counter(q.device).fill_(4242)
+    out, lse = attention_launch.forward(q.detach(), k.detach(), v.detach(), h, dropout_p=p, salt=99)
+    g = torch.randn_like(out)
+    dq, dk, dv = attention_launch.backward(q.detach(), k.detach(), v.detach(), out, g, lse, h, p, 99)
+    keep = attention_launch.dropout_keep(b * h, lq, lk, p, 99, q.device) if p > 0 else None
+    q64, k64, v64 = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+    ref = attention_sm100._math(q64, k64, v64, h, p, False, False, keep)
+    rq, rk, rv = torch.autograd.grad(ref, (q64, k64, v64), g.double())
+    for name, got, exp in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+        err = ((got.double() - exp).abs().max() / exp.abs().max()).item()
+        assert err < 2e-4, f"{name}: rel err {err:.2e}"
