@@ -85,7 +85,11 @@ __host__ __device__ constexpr int prod_b(int ns, int p) {
   return ns == 1 ? 0 : ns == 2 ? (p == 1 ? 1 : 0) : (p == 0 ? 1 : p == 1 ? 0 : p == 2 ? 2 : p == 3 ? 0 : p == 4 ? 1 : 0);
 }
 
-template <int NSPLIT, int BN, int STAGES, bool FP16>
+// MN = false: C = A B^T with K-contiguous operands ("NT").
+// MN = true : both operands are stored with the contraction index as the ROW index (A planes
+//             [kc][m], B planes [kc][n]) -- the weight-gradient form dW = dY^T X, which then needs no
+//             transposed copies of dY and X.
+template <int NSPLIT, int BN, int STAGES, bool FP16, bool MN>
 __global__ void __launch_bounds__(256, 1)
 gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, int b_batched, int ksplit,
                const float *__restrict__ bias, int relu, float *__restrict__ c, long long ldc,
@@ -135,16 +139,27 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
         unsigned char *st = smem + (size_t)s * STAGE;
 #pragma unroll
         for (int p = 0; p < NSPLIT; ++p) {
-          tma_load_3d(st + p * A_TILE, &maps.a[p], &full_bar[s], (kb0 + kb) * BK, m0, batch);
-          tma_load_3d(st + NSPLIT * A_TILE + p * B_TILE, &maps.b[p], &full_bar[s], (kb0 + kb) * BK, n0,
-                      b_batched ? batch : 0);
+          if (!MN) {
+            tma_load_3d(st + p * A_TILE, &maps.a[p], &full_bar[s], (kb0 + kb) * BK, m0, batch);
+            tma_load_3d(st + NSPLIT * A_TILE + p * B_TILE, &maps.b[p], &full_bar[s], (kb0 + kb) * BK, n0,
+                        b_batched ? batch : 0);
+          } else {
+            // [64 contraction rows x 64 mn] boxes, one per 64-wide slab of the tile
+#pragma unroll
+            for (int g = 0; g < BM / 64; ++g)
+              tma_load_3d(st + p * A_TILE + g * 8192, &maps.a[p], &full_bar[s], m0 + g * 64, (kb0 + kb) * BK, batch);
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g)
+              tma_load_3d(st + NSPLIT * A_TILE + p * B_TILE + g * 8192, &maps.b[p], &full_bar[s], n0 + g * 64,
+                          (kb0 + kb) * BK, b_batched ? batch : 0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc_f16(FP16 ? 1 : 0, BM, BN);
+      constexpr uint32_t idesc = umma_idesc_f16(FP16 ? 1 : 0, BM, BN, MN ? 1 : 0, MN ? 1 : 0);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -153,11 +168,13 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
         unsigned char *st = smem + (size_t)s * STAGE;
 #pragma unroll
         for (int p = 0; p < n_products(NSPLIT); ++p) {
-          const uint64_t ad = umma_smem_desc_k_sw128(st + prod_a(NSPLIT, p) * A_TILE);
-          const uint64_t bd = umma_smem_desc_k_sw128(st + NSPLIT * A_TILE + prod_b(NSPLIT, p) * B_TILE);
+          const void *at = st + prod_a(NSPLIT, p) * A_TILE, *bt = st + NSPLIT * A_TILE + prod_b(NSPLIT, p) * B_TILE;
+          const uint64_t ad = MN ? umma_smem_desc_mn_sw128(at) : umma_smem_desc_k_sw128(at);
+          const uint64_t bd = MN ? umma_smem_desc_mn_sw128(bt) : umma_smem_desc_k_sw128(bt);
+          constexpr uint32_t KSTEP = MN ? 16 * 128 : 32;  // bytes per 16-deep k-step
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk)
-            umma_f16(tmem_base, umma_desc_advance(ad, kk * 32), umma_desc_advance(bd, kk * 32), idesc,
+            umma_f16(tmem_base, umma_desc_advance(ad, kk * KSTEP), umma_desc_advance(bd, kk * KSTEP), idesc,
                      (uint32_t)((kb | p | kk) != 0));
         }
         umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
@@ -223,7 +240,7 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
   if (warp == 2) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
 }
 
-template <int NSPLIT, int BN, int STAGES, bool FP16>
+template <int NSPLIT, int BN, int STAGES, bool FP16, bool MN = false>
 int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_batched, const float *bias, int relu,
                 float *c, long long ldc, long long c_batch_stride, cudaStream_t s) {
   // split-K when the output has few tiles but the contraction is long (weight gradients)
@@ -243,7 +260,7 @@ int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_b
     if (ez != cudaSuccess) return (int)ez;
   }
   constexpr size_t smem = (size_t)STAGES * NSPLIT * (BM * BK * 2 + BN * BK * 2) + 1024;
-  auto kern = gemm_nt_kernel<NSPLIT, BN, STAGES, FP16>;
+  auto kern = gemm_nt_kernel<NSPLIT, BN, STAGES, FP16, MN>;
   static bool configured = false;  // once per template instance
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -329,6 +346,34 @@ int coda_gemm_nt(int nsplit, int is_fp16, int batch, int m, int n, int kpad, con
   if (bn == 64) CODA_GEMM(3, 64, 3, false);
   CODA_GEMM(3, 128, 2, false);
 #undef CODA_GEMM
+}
+
+
+int coda_gemm_tn(int nsplit, int mc, int m, int n, const void *a, long long a_plane_stride, int lda,
+                 const void *b, long long b_plane_stride, int ldb, float *c, long long ldc, void *stream) {
+  // C[m][n] = sum_r A[r][m] * B[r][n], r < mc;  A planes [nsplit][mc][lda], B planes [nsplit][mc][ldb]
+  if (nsplit < 1 || nsplit > 3 || mc < 0 || m < 0 || n < 0 || lda % 64 != 0 || ldb % 64 != 0) return CODA_EINVAL;
+  if (m == 0 || n == 0) return CODA_OK;
+  if (!a || !b || !c || mc == 0 || lda < m || ldb < n) return CODA_EINVAL;
+  const int bn = n <= 64 ? 64 : 128;
+  GemmMaps maps;
+  const char *ap = (const char *)a, *bp = (const char *)b;
+  for (int p = 0; p < nsplit; ++p) {
+    // tensors [1][mc rows][lda cols]; box = [64 rows][64 cols]
+    int st = make_tmap_k_major_16b(&maps.a[p], ap + (size_t)p * a_plane_stride * 2, 0, lda, mc, 1, lda, 0, 64);
+    if (st != CODA_OK) return st;
+    st = make_tmap_k_major_16b(&maps.b[p], bp + (size_t)p * b_plane_stride * 2, 0, ldb, mc, 1, ldb, 0, 64);
+    if (st != CODA_OK) return st;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int kpad = (mc + 63) / 64 * 64;  // contraction length in 64-row blocks (rows >= mc read as zero)
+#define CODA_GEMM_TN(NS, BN_, ST) \
+  return launch_gemm<NS, BN_, ST, false, true>(maps, 1, m, n, kpad, 0, nullptr, 0, c, ldc, 0, s)
+  if (nsplit == 1) { if (bn == 64) CODA_GEMM_TN(1, 64, 6); CODA_GEMM_TN(1, 128, 6); }
+  if (nsplit == 2) { if (bn == 64) CODA_GEMM_TN(2, 64, 4); CODA_GEMM_TN(2, 128, 3); }
+  if (bn == 64) CODA_GEMM_TN(3, 64, 3);
+  CODA_GEMM_TN(3, 128, 2);
+#undef CODA_GEMM_TN
 }
 
 }  // extern "C"

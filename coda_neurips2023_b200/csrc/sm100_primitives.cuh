@@ -137,12 +137,27 @@ __device__ __forceinline__ uint64_t umma_smem_desc_k_sw128(const void *tile) {
   d |= (uint64_t)2 << 61;                             // layout type SWIZZLE_128B
   return d;
 }
+// MN-major operand tile (the contraction index is the ROW index of the stored tensor): the tile is
+// a sequence of [64 k-rows x 64 mn] boxes (8 KB each, 128B-swizzled rows of 64 contiguous MN
+// elements).  Canonical layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in elements (cute
+// mma_traits_sm100.hpp): 8-row K groups SBO = 1024 B apart, 64-wide MN groups LBO = 8192 B apart.
+__device__ __forceinline__ uint64_t umma_smem_desc_mn_sw128(const void *tile) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(tile) & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;                   // leading byte offset: next 64 MN elements
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: next 8 K rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
 // advance the start address by `bytes` inside the swizzle atom (k-steps of 32 B)
 __device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
 
 // instruction descriptor for kind::f16: fp32 accumulate, K-major A and B
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int is_fp16, int m, int n) {
-  return (1u << 4)                                 // c_format = F32
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int is_fp16, int m, int n, int a_mn = 0, int b_mn = 0) {
+  return ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16)  // operand majors: 0 = K-major, 1 = MN-major
+         | (1u << 4)                                 // c_format = F32
          | ((is_fp16 ? 0u : 1u) << 7)              // a_format (0 = F16, 1 = BF16)
          | ((is_fp16 ? 0u : 1u) << 10)             // b_format
          | ((uint32_t)(n >> 3) << 17)              // n_dim

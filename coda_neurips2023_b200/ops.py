@@ -248,6 +248,24 @@ def gemm_nt(a_planes: torch.Tensor, b_planes: torch.Tensor, m: int, n: int, bias
     return out
 
 
+def gemm_tn(a_planes: torch.Tensor, b_planes: torch.Tensor, m: int, n: int) -> torch.Tensor:
+    """C (m, n) = sum_r A[r, :m]^T B[r, :n] from ROW-packed planes (nsplit, 1, rows, pad64(cols)):
+    the weight-gradient form dW = dY^T X on MN-major tensor-core operands (no transposed copies)."""
+    _need_cuda(a_planes, "gemm_tn")
+    nsplit, _, mc, lda = a_planes.shape
+    assert b_planes.shape[0] == nsplit and b_planes.shape[2] == mc
+    ldb = b_planes.shape[3]
+    out = torch.empty((m, n), dtype=torch.float32, device=a_planes.device)
+    with torch.cuda.device(a_planes.device):
+        st = lib().coda_gemm_tn(_i(nsplit), _i(mc), _i(m), _i(n), ptr(a_planes), _ll(a_planes.stride(0)), _i(lda),
+                                ptr(b_planes), _ll(b_planes.stride(0)), _i(ldb), ptr(out), _ll(n), stream_of(a_planes))
+    check(st, "gemm_tn")
+    return out
+
+
+USE_TN_WGRAD = True  # weight gradients from the row-packed operands (MN-major MMA); False: transposed packs
+
+
 # --------------------------------------------------------------------------- Linear on the tcgen05 GEMM
 _WEIGHT_EPOCH = 0
 _WEIGHT_CACHE: dict = {}
@@ -282,28 +300,37 @@ class _Linear(torch.autograd.Function):
         n = weight.shape[0]
         xa = pack_split(x, m, k, x.stride(0), 1, nsplit)
         y = gemm_nt(xa, _packed_weight(weight, False, nsplit), m, n, bias=bias, relu=relu)[0]
-        ctx.save_for_backward(x, weight, y if relu else None)
+        # the backward needs x only as a GEMM operand: keep its packed planes instead of the fp32 tensor
+        keep_planes = USE_TN_WGRAD and weight.requires_grad
+        ctx.save_for_backward(None if keep_planes else x, weight, y if relu else None, xa if keep_planes else None)
+        ctx.xshape = (m, k)
         ctx.has_bias, ctx.relu, ctx.nsplit = bias is not None, relu, nsplit
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, y = ctx.saved_tensors
+        x, weight, y, xa = ctx.saved_tensors
         nsplit = ctx.nsplit
         dy = dy.contiguous()
         if ctx.relu:
             dy = dy * (y > 0).to(dy.dtype)
-        m, k = x.shape
+        m, k = ctx.xshape
         n = weight.shape[0]
         dx = dw = db = None
+        dya = None
+        if ctx.needs_input_grad[0] or (ctx.needs_input_grad[1] and xa is not None):
+            dya = pack_split(dy, m, n, n, 1, nsplit)   # row-packed dY: operand of both gradients
         if ctx.needs_input_grad[0]:
             # dX (m, k) = dY (m, n) @ W (n, k): B operand = W^T planes (rows k, contraction n)
-            dx = gemm_nt(pack_split(dy, m, n, n, 1, nsplit), _packed_weight(weight, True, nsplit), m, k)[0]
+            dx = gemm_nt(dya, _packed_weight(weight, True, nsplit), m, k)[0]
         if ctx.needs_input_grad[1]:
-            # dW (n, k) = dY^T (n, m) @ X (m, k): both operands contracted over m -> transposed packs
-            dyt = pack_split(dy, n, m, 1, n, nsplit)
-            xt = pack_split(x, k, m, 1, x.stride(0), nsplit)
-            dw = gemm_nt(dyt, xt, n, k)[0]
+            if xa is not None:
+                # dW (n, k) = sum_m dY[m, n] X[m, k]: contraction over the ROWS of both packed operands
+                dw = gemm_tn(dya, xa, n, k)
+            else:
+                dyt = pack_split(dy, n, m, 1, n, nsplit)
+                xt = pack_split(x, k, m, 1, x.stride(0), nsplit)
+                dw = gemm_nt(dyt, xt, n, k)[0]
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(dim=0)
         return dx, dw, db, None, None

@@ -48,6 +48,15 @@ int coda_gemm_nt(int nsplit, int is_fp16, int batch, int m, int n, int kpad, con
                  long long b_plane_stride, long long b_batch_stride, const float *bias, int relu,
                  float *c, long long ldc, long long c_batch_stride, void *stream);
 
+/*
+ * "TN" form for weight gradients: C[m][n] = sum_{r < mc} A[r][m] * B[r][n], with A planes
+ * [nsplit][mc][lda] and B planes [nsplit][mc][ldb] (row-major, lda / ldb multiples of 64), i.e. the
+ * contraction runs over ROWS of both stored operands (MN-major tensor-core operands): dW = dY^T X
+ * straight from the row-packed dY and X, no transposed copies.  Split-K over mc when m x n is small.
+ */
+int coda_gemm_tn(int nsplit, int mc, int m, int n, const void *a, long long a_plane_stride, int lda,
+                 const void *b, long long b_plane_stride, int ldb, float *c, long long ldc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,3 +101,16 @@ def test_linear_autograd_matches_torch():
         rx, rw, rb = torch.autograd.grad(ref, (x, w, b), g.double())
         for got, exp in ((gx, rx), (gw, rw), (gb, rb)):   # fp32 accumulation over up to 3000 terms
             assert ((got.double() - exp.double()).abs().max() / exp.abs().max()).item() < 3e-5
+
+
+@pytest.mark.parametrize("mc,m,n", [(64, 128, 128), (1000, 128, 64), (3000, 512, 256), (200000, 256, 128), (77, 13, 3)])
+def test_gemm_tn_mn_major_operands(mc, m, n):
+    """C = A^T B from row-packed planes (MN-major tensor-core operands): the weight-gradient form"""
+    torch.manual_seed(mc + m)
+    a = torch.randn(mc, m, device="cuda")
+    b = torch.randn(mc, n, device="cuda")
+    ap = ops.pack_split(a, mc, m, m, 1, 3)
+    bp = ops.pack_split(b, mc, n, n, 1, 3)
+    c = ops.gemm_tn(ap, bp, m, n)
+    ref = a.double().t() @ b.double()
+    assert ((c.double() - ref).abs().max() / ref.abs().max()).item() < 2e-5
