@@ -24,17 +24,18 @@ from torch import nn
 from .. import ops
 
 
-def _linear(x, w, b):
-    """fp16 activations x fp16 weights on the fp16 tcgen05 path; fp32 (CPU checks) through torch."""
+def _linear(x, w, b, quick_gelu=False):
+    """fp16 activations x fp16 weights on the fp16 tcgen05 path (fp16 written by the epilogue,
+    QuickGELU fused); fp32 (CPU checks, small test models) through torch."""
     if x.is_cuda and x.dtype == torch.float16 and x.shape[-1] % 64 == 0:
-        return ops.linear(x, w, b)
-    return F.linear(x, w, b)
+        return ops.linear(x, w, b, quick_gelu=quick_gelu)
+    y = F.linear(x, w, b)
+    return y * torch.sigmoid(1.702 * y) if quick_gelu else y
 
 
 class _MLP(nn.Sequential):
     def forward(self, x):
-        h = _linear(x, self.c_fc.weight, self.c_fc.bias)
-        h = self.gelu(h)
+        h = _linear(x, self.c_fc.weight, self.c_fc.bias, quick_gelu=True)
         return _linear(h, self.c_proj.weight, self.c_proj.bias)
 
 
@@ -62,7 +63,12 @@ class _PackedSelfAttention(nn.Module):
 
     def forward(self, x: torch.Tensor, causal: bool = False):
         q, k, v = _linear(x, self.in_proj_weight, self.in_proj_bias).split(self.embed_dim, dim=-1)
-        out = ops.attention(q, k, v, self.num_heads, 0.0, False, causal=causal)
+        if x.is_cuda and x.dtype == torch.float16 and not causal and self.embed_dim // self.num_heads == 64:
+            # image tower: fused tcgen05 attention on 2 bf16 planes (16 mantissa bits >= fp16's 11)
+            from .. import attention_launch
+            out = attention_launch.forward(q.float(), k.float(), v.float(), self.num_heads, nsplit=2)[0].to(x.dtype)
+        else:
+            out = ops.attention(q, k, v, self.num_heads, 0.0, False, causal=causal)
         return _linear(out, self.out_proj.weight, self.out_proj.bias)
 
 

@@ -92,8 +92,10 @@ __host__ __device__ constexpr int prod_b(int ns, int p) {
 template <int NSPLIT, int BN, int STAGES, bool FP16, bool MN>
 __global__ void __launch_bounds__(256, 1)
 gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, int b_batched, int ksplit,
-               const float *__restrict__ bias, int relu, float *__restrict__ c, long long ldc,
+               const float *__restrict__ bias, int act, int out_half, void *__restrict__ c_void, long long ldc,
                long long c_batch_stride) {
+  float *__restrict__ c = reinterpret_cast<float *>(c_void);
+  const int relu = act == 1;
   constexpr int A_TILE = BM * BK * 2;
   constexpr int B_TILE = BN * BK * 2;
   constexpr int STAGE = NSPLIT * (A_TILE + B_TILE);
@@ -197,7 +199,24 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
       tmem_ld_wait();
       if (row < m) {
         const int col0 = n0 + c0;
-        if (ksplit > 1) {
+        if (out_half) {
+          // fp16 output (CLIP ViT path), optional QuickGELU x * sigmoid(1.702 x)
+          __half *hrow = reinterpret_cast<__half *>(c_void) + (size_t)batch * c_batch_stride + (size_t)row * ldc;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
+            const int col = col0 + j;
+            if (bias) { if (col < n) v0 += __ldg(bias + col); if (col + 1 < n) v1 += __ldg(bias + col + 1); }
+            if (act == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            if (act == 2) { v0 = v0 / (1.0f + __expf(-1.702f * v0)); v1 = v1 / (1.0f + __expf(-1.702f * v1)); }
+            if (col + 1 < n && (ldc & 1) == 0) {
+              *reinterpret_cast<__half2 *>(hrow + col) = __floats2half2_rn(v0, v1);
+            } else {
+              if (col < n) hrow[col] = __float2half_rn(v0);
+              if (col + 1 < n) hrow[col + 1] = __float2half_rn(v1);
+            }
+          }
+        } else if (ksplit > 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = col0 + j;
@@ -242,12 +261,13 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
 
 template <int NSPLIT, int BN, int STAGES, bool FP16, bool MN = false>
 int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_batched, const float *bias, int relu,
-                float *c, long long ldc, long long c_batch_stride, cudaStream_t s) {
+                void *c_out, long long ldc, long long c_batch_stride, cudaStream_t s, int out_half = 0) {
+  float *c = reinterpret_cast<float *>(c_out);
   // split-K when the output has few tiles but the contraction is long (weight gradients)
   const long long tiles = (long long)((m + BM - 1) / BM) * ((n + BN - 1) / BN) * batch;
   const int nkb_total = kpad / BK;
   int ksplit = 1;
-  if (!relu && tiles < 148 && nkb_total >= 32) {
+  if (!relu && !out_half && tiles < 148 && nkb_total >= 32) {
     ksplit = (int)((2 * 148 + tiles - 1) / tiles);
     if (ksplit > nkb_total / 8) ksplit = nkb_total / 8;
     if (ksplit < 1) ksplit = 1;
@@ -268,7 +288,7 @@ int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_b
     configured = true;
   }
   const dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, batch * ksplit);
-  kern<<<grid, 256, smem, s>>>(maps, m, n, kpad, b_batched, ksplit, bias, relu, c, ldc, c_batch_stride);
+  kern<<<grid, 256, smem, s>>>(maps, m, n, kpad, b_batched, ksplit, bias, relu, out_half, c_out, ldc, c_batch_stride);
   return launch_status();
 }
 
@@ -312,6 +332,14 @@ int coda_gemm_nt(int nsplit, int is_fp16, int batch, int m, int n, int kpad, con
                  long long a_plane_stride, long long a_batch_stride, const void *b, long long b_plane_stride,
                  long long b_batch_stride, const float *bias, int relu, float *c, long long ldc,
                  long long c_batch_stride, void *stream) {
+  return coda_gemm_nt_ex(nsplit, is_fp16, batch, m, n, kpad, a, a_plane_stride, a_batch_stride, b, b_plane_stride,
+                         b_batch_stride, bias, relu, 0, c, ldc, c_batch_stride, stream);
+}
+
+int coda_gemm_nt_ex(int nsplit, int is_fp16, int batch, int m, int n, int kpad, const void *a,
+                    long long a_plane_stride, long long a_batch_stride, const void *b, long long b_plane_stride,
+                    long long b_batch_stride, const float *bias, int relu, int out_half, void *c, long long ldc,
+                    long long c_batch_stride, void *stream) {
   if (nsplit < 1 || nsplit > 3 || batch < 0 || m < 0 || n < 0 || kpad < 0 || kpad % 64 != 0) return CODA_EINVAL;
   if (is_fp16 && nsplit != 1) return CODA_EINVAL;
   if (batch == 0 || m == 0 || n == 0) return CODA_OK;
@@ -330,7 +358,7 @@ int coda_gemm_nt(int nsplit, int is_fp16, int batch, int m, int n, int kpad, con
   cudaStream_t s = (cudaStream_t)stream;
   const int bb = b_batch_stride ? 1 : 0;
 #define CODA_GEMM(NS, BN_, ST, F16) \
-  return launch_gemm<NS, BN_, ST, F16>(maps, batch, m, n, kpad, bb, bias, relu, c, ldc, c_batch_stride, s)
+  return launch_gemm<NS, BN_, ST, F16>(maps, batch, m, n, kpad, bb, bias, relu, c, ldc, c_batch_stride, s, out_half)
   if (is_fp16) {
     if (bn == 64) CODA_GEMM(1, 64, 6, true);
     CODA_GEMM(1, 128, 6, true);

@@ -227,7 +227,7 @@ def pack_split(x: torch.Tensor, rows: int, k: int, row_stride: int, k_stride: in
 
 
 def gemm_nt(a_planes: torch.Tensor, b_planes: torch.Tensor, m: int, n: int, bias=None, relu: bool = False,
-            out: torch.Tensor | None = None) -> torch.Tensor:
+            out: torch.Tensor | None = None, act: int | None = None, out_dtype=torch.float32) -> torch.Tensor:
     """C[b] = A[b] @ B[b]^T (+ bias) from packed planes (nsplit, batch, rows, kpad); B may have batch 1
     (shared weights).  fp16 planes (nsplit == 1) select the fp16 tensor-core path.  Returns fp32 (batch, m, n)."""
     _need_cuda(a_planes, "gemm_nt")
@@ -237,13 +237,15 @@ def gemm_nt(a_planes: torch.Tensor, b_planes: torch.Tensor, m: int, n: int, bias
     bb = b_planes.shape[1]
     assert bb in (1, batch)
     if out is None:
-        out = torch.empty((batch, m, n), dtype=torch.float32, device=a_planes.device)
+        out = torch.empty((batch, m, n), dtype=out_dtype, device=a_planes.device)
+    if act is None:
+        act = 1 if relu else 0
     with torch.cuda.device(a_planes.device):
-        st = lib().coda_gemm_nt(
+        st = lib().coda_gemm_nt_ex(
             _i(nsplit), _i(1 if is_fp16 else 0), _i(batch), _i(m), _i(n), _i(kpad), ptr(a_planes),
             _ll(a_planes.stride(0)), _ll(a_planes.stride(1)), ptr(b_planes), _ll(b_planes.stride(0)),
-            _ll(b_planes.stride(1) if bb > 1 else 0), ptr(bias), _i(1 if relu else 0), ptr(out), _ll(out.stride(1)),
-            _ll(out.stride(0)), stream_of(a_planes))
+            _ll(b_planes.stride(1) if bb > 1 else 0), ptr(bias), _i(act), _i(1 if out.dtype == torch.float16 else 0),
+            ptr(out), _ll(out.stride(1)), _ll(out.stride(0)), stream_of(a_planes))
     check(st, "gemm_nt")
     return out
 
@@ -336,7 +338,21 @@ class _Linear(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
-def linear(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool = False, nsplit: int | None = None):
+_BIAS32: dict = {}
+
+
+def _bias_fp32(bias):
+    """fp32 copy of a (frozen, fp16) bias, cached: the epilogue adds the bias in fp32."""
+    key = (bias.data_ptr(), bias._version)
+    if key not in _BIAS32:
+        if len(_BIAS32) > 256:
+            _BIAS32.clear()
+        _BIAS32[key] = bias.detach().float()
+    return _BIAS32[key]
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool = False, nsplit: int | None = None,
+           quick_gelu: bool = False):
     """y = x @ weight^T + bias over the last dim of x, on the tcgen05 GEMM (fp32 in / out, bf16
     split-operand accumulation); fp16 x / weight take the fp16 tensor-core path (inference only)."""
     _need_cuda(x, "linear")
@@ -348,8 +364,9 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool = False,
         assert weight.dtype == torch.float16 and k % 64 == 0, "fp16 path needs fp16 weights and K % 64 == 0"
         x2 = x2.contiguous()
         y = gemm_nt(x2.view(1, 1, x2.shape[0], k), weight.detach().contiguous().view(1, 1, n, k), x2.shape[0], n,
-                    bias=None if bias is None else bias.float(), relu=relu)[0]
-        return y.to(torch.float16).reshape(*lead, n)
+                    bias=None if bias is None else _bias_fp32(bias), act=2 if quick_gelu else (1 if relu else 0),
+                    out_dtype=torch.float16)[0]
+        return y.reshape(*lead, n)
     if x2.stride(-1) != 1:
         x2 = x2.contiguous()
     w2 = weight.reshape(n, -1)

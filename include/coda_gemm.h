@@ -48,6 +48,13 @@ int coda_gemm_nt(int nsplit, int is_fp16, int batch, int m, int n, int kpad, con
                  long long b_plane_stride, long long b_batch_stride, const float *bias, int relu,
                  float *c, long long ldc, long long c_batch_stride, void *stream);
 
+/* Extended form: `act` 0 none / 1 ReLU / 2 QuickGELU (x * sigmoid(1.702 x), CLIP/clip/model.py:263-265);
+ * out_half != 0 writes C as IEEE fp16 (the CLIP ViT path keeps activations in fp16). */
+int coda_gemm_nt_ex(int nsplit, int is_fp16, int batch, int m, int n, int kpad, const void *a,
+                    long long a_plane_stride, long long a_batch_stride, const void *b,
+                    long long b_plane_stride, long long b_batch_stride, const float *bias, int act,
+                    int out_half, void *c, long long ldc, long long c_batch_stride, void *stream);
+
 /*
  * "TN" form for weight gradients: C[m][n] = sum_{r < mc} A[r][m] * B[r][n], with A planes
  * [nsplit][mc][lda] and B planes [nsplit][mc][ldb] (row-major, lda / ldb multiples of 64), i.e. the

@@ -114,3 +114,18 @@ def test_gemm_tn_mn_major_operands(mc, m, n):
     c = ops.gemm_tn(ap, bp, m, n)
     ref = a.double().t() @ b.double()
     assert ((c.double() - ref).abs().max() / ref.abs().max()).item() < 2e-5
+
+
+def test_gemm_fp16_output_and_quick_gelu():
+    torch.manual_seed(5)
+    x = (torch.randn(700, 768, device="cuda") * 0.5).half()
+    w = (torch.randn(3072, 768, device="cuda") * 0.03).half()
+    b = (torch.randn(3072, device="cuda") * 0.1).half()
+    y = ops.linear(x, w, b, quick_gelu=True)
+    assert y.dtype == torch.float16
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    ref = ref * torch.sigmoid(1.702 * ref)
+    assert ((y.double() - ref).abs().max() / ref.abs().max()).item() < 2e-3
+    y2 = ops.linear(x, w, None)
+    ref2 = torch.nn.functional.linear(x.double(), w.double())
+    assert ((y2.double() - ref2).abs().max() / ref2.abs().max()).item() < 2e-3
