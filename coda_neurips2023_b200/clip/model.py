@@ -116,8 +116,16 @@ class VisionTransformer(nn.Module):
 
     def forward(self, x: torch.Tensor, im_name=None, max_w=None, if_pool=True, if_early_feat=False):
         """(N, 3, R, R) -> (cls embedding (N, output_dim), all tokens (N, grid^2 + 1, output_dim))"""
-        x = self.conv1(x)                                   # (N, width, grid, grid)
-        x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
+        ps = self.conv1.kernel_size[0]
+        if x.is_cuda and x.dtype == torch.float16 and x.shape[-1] % ps == 0 and (3 * ps * ps) % 64 == 0:
+            # the patch embedding (kernel = stride = patch size, no bias) is a GEMM over unfolded patches
+            n, c, hh, ww = x.shape
+            g = hh // ps
+            patches = x.view(n, c, g, ps, g, ps).permute(0, 2, 4, 1, 3, 5).reshape(n * g * g, c * ps * ps)
+            x = _linear(patches, self.conv1.weight.view(self.conv1.weight.shape[0], -1), None).view(n, g * g, -1)
+        else:
+            x = self.conv1(x)                               # (N, width, grid, grid)
+            x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
         cls = self.class_embedding.to(x.dtype).expand(x.shape[0], 1, -1)
         x = torch.cat([cls, x], dim=1) + self.positional_embedding.to(x.dtype)
         x = self.ln_pre(x)
