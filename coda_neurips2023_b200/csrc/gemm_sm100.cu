@@ -202,18 +202,30 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
         if (out_half) {
           // fp16 output (CLIP ViT path), optional QuickGELU x * sigmoid(1.702 x)
           __half *hrow = reinterpret_cast<__half *>(c_void) + (size_t)batch * c_batch_stride + (size_t)row * ldc;
+          const bool full = col0 + 32 <= n && (ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(hrow + col0) & 15) == 0);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
-            const int col = col0 + j;
-            if (bias) { if (col < n) v0 += __ldg(bias + col); if (col + 1 < n) v1 += __ldg(bias + col + 1); }
-            if (act == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            if (act == 2) { v0 = v0 / (1.0f + __expf(-1.702f * v0)); v1 = v1 / (1.0f + __expf(-1.702f * v1)); }
-            if (col + 1 < n && (ldc & 1) == 0) {
-              *reinterpret_cast<__half2 *>(hrow + col) = __floats2half2_rn(v0, v1);
+          for (int j0 = 0; j0 < 32; j0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const int col = col0 + j0 + t;
+              float x = __uint_as_float(r[j0 + t]);
+              if (bias && col < n) x += __ldg(bias + col);
+              if (act == 1) x = fmaxf(x, 0.f);
+              if (act == 2) x = x / (1.0f + __expf(-1.702f * x));
+              v[t] = x;
+            }
+            if (full) {  // 8 halves = one 16-byte store
+              uint4 pk;
+              __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+              __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+              pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+              pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+              *reinterpret_cast<uint4 *>(hrow + col0 + j0) = pk;
             } else {
-              if (col < n) hrow[col] = __float2half_rn(v0);
-              if (col + 1 < n) hrow[col + 1] = __float2half_rn(v1);
+#pragma unroll
+              for (int t = 0; t < 8; ++t)
+                if (col0 + j0 + t < n) hrow[col0 + j0 + t] = __float2half_rn(v[t]);
             }
           }
         } else if (ksplit > 1) {

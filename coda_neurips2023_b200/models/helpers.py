@@ -86,18 +86,10 @@ class GenericMLP(nn.Module):
             if param.dim() > 1:  # skips the norm layers
                 func(param)
 
-    def forward(self, x):
-        """(B, C, L) for the conv variant, (..., C) for the linear one.  The 1x1 convolutions are
-        GEMMs over the channel dim: run channels-last as (B*L, C) rows on ops.linear (tcgen05), with
-        BatchNorm1d / ReLU / Dropout applied to the same 2-D tensor; ReLU directly after a dense
-        layer is fused into the GEMM epilogue."""
-        conv = isinstance(self.layers[0], nn.Conv1d)
-        if conv:
-            b, c, l = x.shape
-            h = x.transpose(1, 2).reshape(b * l, c)
-        else:
-            lead = x.shape[:-1]
-            h = x.reshape(-1, x.shape[-1])
+    def forward_rows(self, h):
+        """The stack on channels-last rows (N, C_in) -> (N, C_out).  The 1x1 convolutions are GEMMs over
+        the channel dim (ops.linear, tcgen05); BatchNorm1d / ReLU / Dropout act on the same 2-D tensor;
+        a ReLU directly after a dense layer is fused into the GEMM epilogue."""
         mods = list(self.layers)
         i = 0
         while i < len(mods):
@@ -106,15 +98,21 @@ class GenericMLP(nn.Module):
                 fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
                 h = ops.linear(h, mod.weight.reshape(mod.weight.shape[0], -1), mod.bias, relu=fuse)
                 i += 2 if fuse else 1
-            elif isinstance(mod, nn.GroupNorm):  # "ln" over conv channels: per-sample norm, keep the module
-                h = mod(h.view(b, l, -1).transpose(1, 2)).transpose(1, 2).reshape(b * l, -1)
-                i += 1
+            elif isinstance(mod, nn.GroupNorm):
+                raise NotImplementedError("GroupNorm ('ln' on a conv MLP) is not used on the CoDA path")
             else:                                  # BatchNorm1d on (N, C), ReLU, Dropout, LayerNorm
                 h = mod(h)
                 i += 1
-        if conv:
+        return h
+
+    def forward(self, x):
+        """(B, C, L) for the conv variant, (..., C) for the linear one."""
+        if isinstance(self.layers[0], nn.Conv1d):
+            b, c, l = x.shape
+            h = self.forward_rows(x.transpose(1, 2).reshape(b * l, c))
             return h.view(b, l, -1).transpose(1, 2)
-        return h.view(*lead, -1)
+        lead = x.shape[:-1]
+        return self.forward_rows(x.reshape(-1, x.shape[-1])).view(*lead, -1)
 
 
 def get_clones(module, N):

@@ -300,19 +300,19 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
     def get_box_predictions(self, query_xyz, point_cloud_dims, box_features, point_clouds, inputs):
         """box_features (num_layers, nqueries, batch, channel) -> per-layer prediction dicts
         (reference :1634-1740)."""
-        box_features = box_features.permute(0, 2, 3, 1)
-        num_layers, batch, channel, num_queries = box_features.shape
-        box_features = box_features.reshape(num_layers * batch, channel, num_queries)
+        num_layers, num_queries, batch, channel = box_features.shape
+        # the reference runs the heads on (num_layers*batch, channel, nqueries) conv maps; as rows
+        # (layer, batch, query) x channel the six heads share ONE packed GEMM operand and their outputs
+        # land directly in (num_layers, batch, nqueries, out) order
+        rows = box_features.permute(0, 2, 1, 3).reshape(num_layers * batch * num_queries, channel)
 
         def head(name):
-            return self.mlp_heads[name](box_features).transpose(1, 2).reshape(num_layers, batch, num_queries, -1)
+            return self.mlp_heads[name].forward_rows(rows).view(num_layers, batch, num_queries, -1)
 
         cls_logits = head("sem_cls_head")
         text_correlation_embedding = head("text_correlation_head")
-        center_offset = (self.mlp_heads["center_head"](box_features).sigmoid().transpose(1, 2) - 0.5).reshape(
-            num_layers, batch, num_queries, -1)
-        size_normalized = self.mlp_heads["size_head"](box_features).sigmoid().transpose(1, 2).reshape(
-            num_layers, batch, num_queries, -1)
+        center_offset = head("center_head").sigmoid() - 0.5
+        size_normalized = head("size_head").sigmoid()
         angle_logits = head("angle_cls_head")
         angle_residual_normalized = head("angle_residual_head")
         angle_residual = angle_residual_normalized * (np.pi / angle_residual_normalized.shape[-1])

@@ -273,12 +273,31 @@ _WEIGHT_EPOCH = 0
 _WEIGHT_CACHE: dict = {}
 
 
+_ACT_CACHE: dict = {}   # packed planes of activations that several layers consume within one step
+
+
 def invalidate_weight_cache() -> None:
     """Call after parameters were updated through storage the tensors' version counters do not see
-    (the flat-buffer optimiser step of engine.TrainStep)."""
+    (the flat-buffer optimiser step of engine.TrainStep).  Also ends the per-step activation-pack cache."""
     global _WEIGHT_EPOCH
     _WEIGHT_EPOCH += 1
     _WEIGHT_CACHE.clear()
+    _ACT_CACHE.clear()
+
+
+def _packed_rows(x: torch.Tensor, nsplit: int) -> torch.Tensor:
+    """Row-packed planes of a 2-D activation, shared by every layer that consumes the SAME tensor in
+    this step (the six prediction heads read one box-feature tensor, the eight decoder layers project
+    the same encoder memory).  The entry keeps `x` alive, so its address cannot be recycled."""
+    key = (x.data_ptr(), tuple(x.shape), x.stride(0), x._version, nsplit)
+    hit = _ACT_CACHE.get(key)
+    if hit is None:
+        planes = pack_split(x, x.shape[0], x.shape[1], x.stride(0), 1, nsplit)
+        if len(_ACT_CACHE) > 64:
+            _ACT_CACHE.clear()
+        _ACT_CACHE[key] = (planes, x)
+        return planes
+    return hit[0]
 
 
 def _packed_weight(w: torch.Tensor, transposed: bool, nsplit: int) -> torch.Tensor:
@@ -300,7 +319,7 @@ class _Linear(torch.autograd.Function):
     def forward(ctx, x, weight, bias, relu, nsplit):
         m, k = x.shape
         n = weight.shape[0]
-        xa = pack_split(x, m, k, x.stride(0), 1, nsplit)
+        xa = _packed_rows(x, nsplit)
         y = gemm_nt(xa, _packed_weight(weight, False, nsplit), m, n, bias=bias, relu=relu)[0]
         # the backward needs x only as a GEMM operand: keep its packed planes instead of the fp32 tensor
         keep_planes = USE_TN_WGRAD and weight.requires_grad
