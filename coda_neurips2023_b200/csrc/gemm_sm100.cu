@@ -91,29 +91,39 @@ __host__ __device__ constexpr int prod_b(int ns, int p) {
 //             transposed copies of dY and X.
 template <int NSPLIT, int BN, int STAGES, bool FP16, bool MN>
 __global__ void __launch_bounds__(256, 1)
-gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, int b_batched, int ksplit,
-               const float *__restrict__ bias, int act, int out_half, void *__restrict__ c_void, long long ldc,
+gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, int b_batched, int ksplit, int batch_n,
+               const float *__restrict__ bias_in, int act, int out_half, void *__restrict__ c_void, long long ldc,
                long long c_batch_stride) {
+  // PERSISTENT: each CTA walks work items w = blockIdx.x, blockIdx.x + gridDim.x, ...;  a work item is
+  // (m-tile, n-tile, batch, k-split).  The accumulator is double-buffered in TMEM (2 x BN columns) so
+  // the epilogue warps drain tile i while the MMA warp already accumulates tile i+1.
   float *__restrict__ c = reinterpret_cast<float *>(c_void);
   const int relu = act == 1;
   constexpr int A_TILE = BM * BK * 2;
   constexpr int B_TILE = BN * BK * 2;
   constexpr int STAGE = NSPLIT * (A_TILE + B_TILE);
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int batch = blockIdx.z / ksplit, ks = blockIdx.z - batch * ksplit;
-  // split-K: this CTA contracts k-blocks [kb0, kb0 + nkb) and adds its partial tile atomically
+  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
+  const long long nwork = (long long)tiles_m * tiles_n * batch_n * ksplit;
   const int nkb_total = kpad / BK;
   const int per = (nkb_total + ksplit - 1) / ksplit;
-  const int kb0 = ks * per;
-  const int nkb = max(0, min(per, nkb_total - kb0));
+
+  // work item -> coordinates (m fastest: consecutive CTAs share the same B tile in L2)
+  auto decode = [&](long long w, int &m0, int &n0, int &batch, int &ks) {
+    const int tm = (int)(w % tiles_m); w /= tiles_m;
+    const int tn = (int)(w % tiles_n); w /= tiles_n;
+    ks = (int)(w % ksplit);
+    batch = (int)(w / ksplit);
+    m0 = tm * BM; n0 = tn * BN;
+  };
 
   if (warp == 0 && lane == 0) {
 #pragma unroll
@@ -121,10 +131,10 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     mbar_fence_init_cluster();
   }
-  if (warp == 2) tmem_alloc(&tmem_slot, BN < 32 ? 32 : BN);
+  if (warp == 2) tmem_alloc(&tmem_slot, 2 * ACC_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -133,27 +143,33 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE);
-        unsigned char *st = smem + (size_t)s * STAGE;
+      uint32_t it = 0;  // running k-block counter across work items -> stage / phase
+      for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+        int m0, n0, batch, ks;
+        decode(w, m0, n0, batch, ks);
+        const int kb0 = ks * per, nkb = max(0, min(per, nkb_total - kb0));
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE);
+          unsigned char *st = smem + (size_t)s * STAGE;
 #pragma unroll
-        for (int p = 0; p < NSPLIT; ++p) {
-          if (!MN) {
-            tma_load_3d(st + p * A_TILE, &maps.a[p], &full_bar[s], (kb0 + kb) * BK, m0, batch);
-            tma_load_3d(st + NSPLIT * A_TILE + p * B_TILE, &maps.b[p], &full_bar[s], (kb0 + kb) * BK, n0,
-                        b_batched ? batch : 0);
-          } else {
-            // [64 contraction rows x 64 mn] boxes, one per 64-wide slab of the tile
+          for (int p = 0; p < NSPLIT; ++p) {
+            if (!MN) {
+              tma_load_3d(st + p * A_TILE, &maps.a[p], &full_bar[s], (kb0 + kb) * BK, m0, batch);
+              tma_load_3d(st + NSPLIT * A_TILE + p * B_TILE, &maps.b[p], &full_bar[s], (kb0 + kb) * BK, n0,
+                          b_batched ? batch : 0);
+            } else {
+              // [64 contraction rows x 64 mn] boxes, one per 64-wide slab of the tile
 #pragma unroll
-            for (int g = 0; g < BM / 64; ++g)
-              tma_load_3d(st + p * A_TILE + g * 8192, &maps.a[p], &full_bar[s], m0 + g * 64, (kb0 + kb) * BK, batch);
+              for (int g = 0; g < BM / 64; ++g)
+                tma_load_3d(st + p * A_TILE + g * 8192, &maps.a[p], &full_bar[s], m0 + g * 64, (kb0 + kb) * BK, batch);
 #pragma unroll
-            for (int g = 0; g < BN / 64; ++g)
-              tma_load_3d(st + NSPLIT * A_TILE + p * B_TILE + g * 8192, &maps.b[p], &full_bar[s], n0 + g * 64,
-                          (kb0 + kb) * BK, b_batched ? batch : 0);
+              for (int g = 0; g < BN / 64; ++g)
+                tma_load_3d(st + NSPLIT * A_TILE + p * B_TILE + g * 8192, &maps.b[p], &full_bar[s], n0 + g * 64,
+                            (kb0 + kb) * BK, b_batched ? batch : 0);
+            }
           }
         }
       }
@@ -162,113 +178,135 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
     if (lane == 0) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc = umma_idesc_f16(FP16 ? 1 : 0, BM, BN, MN ? 1 : 0, MN ? 1 : 0);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tile_i = 0;
+      for (long long w = blockIdx.x; w < nwork; w += gridDim.x, ++tile_i) {
+        int m0, n0, batch, ks;
+        decode(w, m0, n0, batch, ks);
+        const int kb0 = ks * per, nkb = max(0, min(per, nkb_total - kb0));
+        if (nkb == 0) continue;  // (the epilogue skips it as well)
+        const uint32_t buf = tile_i & 1u, use = tile_i >> 1;
+        mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);  // epilogue drained this accumulator buffer
         tc_fence_after();
-        unsigned char *st = smem + (size_t)s * STAGE;
+        const uint32_t tmem_acc = tmem_base + buf * ACC_COLS;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          unsigned char *st = smem + (size_t)s * STAGE;
 #pragma unroll
-        for (int p = 0; p < n_products(NSPLIT); ++p) {
-          const void *at = st + prod_a(NSPLIT, p) * A_TILE, *bt = st + NSPLIT * A_TILE + prod_b(NSPLIT, p) * B_TILE;
-          const uint64_t ad = MN ? umma_smem_desc_mn_sw128(at) : umma_smem_desc_k_sw128(at);
-          const uint64_t bd = MN ? umma_smem_desc_mn_sw128(bt) : umma_smem_desc_k_sw128(bt);
-          constexpr uint32_t KSTEP = MN ? 16 * 128 : 32;  // bytes per 16-deep k-step
+          for (int p = 0; p < n_products(NSPLIT); ++p) {
+            const void *at = st + prod_a(NSPLIT, p) * A_TILE, *bt = st + NSPLIT * A_TILE + prod_b(NSPLIT, p) * B_TILE;
+            const uint64_t ad = MN ? umma_smem_desc_mn_sw128(at) : umma_smem_desc_k_sw128(at);
+            const uint64_t bd = MN ? umma_smem_desc_mn_sw128(bt) : umma_smem_desc_k_sw128(bt);
+            constexpr uint32_t KSTEP = MN ? 16 * 128 : 32;  // bytes per 16-deep k-step
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk)
-            umma_f16(tmem_base, umma_desc_advance(ad, kk * KSTEP), umma_desc_advance(bd, kk * KSTEP), idesc,
-                     (uint32_t)((kb | p | kk) != 0));
+            for (int kk = 0; kk < BK / 16; ++kk)
+              umma_f16(tmem_acc, umma_desc_advance(ad, kk * KSTEP), umma_desc_advance(bd, kk * KSTEP), idesc,
+                       (uint32_t)((kb | p | kk) != 0));
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        umma_commit(&acc_full[buf]);   // accumulator complete
       }
-      if (nkb > 0) umma_commit(&tmem_full_bar);   // accumulator complete
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp - 4;
-    const int row = m0 + q * 32 + lane;
-    if (nkb > 0) {
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
-    if (ks != 0) bias = nullptr;
-    float *crow = c + (size_t)batch * c_batch_stride + (size_t)row * ldc;
+    uint32_t tile_i = 0;
+    for (long long w = blockIdx.x; w < nwork; w += gridDim.x, ++tile_i) {
+      int m0, n0, batch, ks;
+      decode(w, m0, n0, batch, ks);
+      const int kb0 = ks * per, nkb = max(0, min(per, nkb_total - kb0));
+      if (nkb == 0) continue;
+      const uint32_t buf = tile_i & 1u, use = tile_i >> 1;
+      const int row = m0 + q * 32 + lane;
+      const float *bias = ks == 0 ? bias_in : nullptr;
+      mbar_wait(&acc_full[buf], use & 1u);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * ACC_COLS;
+      float *crow = c + (size_t)batch * c_batch_stride + (size_t)row * ldc;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      if (row < m) {
-        const int col0 = n0 + c0;
-        if (out_half) {
-          // fp16 output (CLIP ViT path), optional QuickGELU x * sigmoid(1.702 x)
-          __half *hrow = reinterpret_cast<__half *>(c_void) + (size_t)batch * c_batch_stride + (size_t)row * ldc;
-          const bool full = col0 + 32 <= n && (ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(hrow + col0) & 15) == 0);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (row < m) {
+          const int col0 = n0 + c0;
+          if (out_half) {
+            // fp16 output (CLIP ViT path), optional QuickGELU x * sigmoid(1.702 x)
+            __half *hrow = reinterpret_cast<__half *>(c_void) + (size_t)batch * c_batch_stride + (size_t)row * ldc;
+            const bool full = col0 + 32 <= n && (ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(hrow + col0) & 15) == 0);
 #pragma unroll
-          for (int j0 = 0; j0 < 32; j0 += 8) {
-            float v[8];
+            for (int j0 = 0; j0 < 32; j0 += 8) {
+              float v[8];
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const int col = col0 + j0 + t;
-              float x = __uint_as_float(r[j0 + t]);
-              if (bias && col < n) x += __ldg(bias + col);
-              if (act == 1) x = fmaxf(x, 0.f);
-              if (act == 2) x = x / (1.0f + __expf(-1.702f * x));
-              v[t] = x;
+              for (int t = 0; t < 8; ++t) {
+                const int col = col0 + j0 + t;
+                float x = __uint_as_float(r[j0 + t]);
+                if (bias && col < n) x += __ldg(bias + col);
+                if (act == 1) x = fmaxf(x, 0.f);
+                if (act == 2) x = x / (1.0f + __expf(-1.702f * x));
+                v[t] = x;
+              }
+              if (full) {  // 8 halves = one 16-byte store
+                uint4 pk;
+                __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+                __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+                pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                *reinterpret_cast<uint4 *>(hrow + col0 + j0) = pk;
+              } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                  if (col0 + j0 + t < n) hrow[col0 + j0 + t] = __float2half_rn(v[t]);
+              }
             }
-            if (full) {  // 8 halves = one 16-byte store
-              uint4 pk;
-              __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-              __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
-              pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
-              pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
-              *reinterpret_cast<uint4 *>(hrow + col0 + j0) = pk;
-            } else {
+          } else if (ksplit > 1) {
 #pragma unroll
-              for (int t = 0; t < 8; ++t)
-                if (col0 + j0 + t < n) hrow[col0 + j0 + t] = __float2half_rn(v[t]);
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              if (col < n) {
+                float v = __uint_as_float(r[j]);
+                if (bias) v += __ldg(bias + col);
+                atomicAdd(crow + col, v);
+              }
             }
-          }
-        } else if (ksplit > 1) {
+          } else if (col0 + 32 <= n && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (col < n) {
-              float v = __uint_as_float(r[j]);
-              if (bias) v += __ldg(bias + col);
-              atomicAdd(crow + col, v);
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                     __uint_as_float(r[j + 3]));
+              if (bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col0 + j));
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+              }
+              if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              *reinterpret_cast<float4 *>(crow + col0 + j) = v;
             }
-          }
-        } else if (col0 + 32 <= n && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(crow + col0) & 15) == 0)) {
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                   __uint_as_float(r[j + 3]));
-            if (bias) {
-              v.x += __ldg(bias + col0 + j); v.y += __ldg(bias + col0 + j + 1);
-              v.z += __ldg(bias + col0 + j + 2); v.w += __ldg(bias + col0 + j + 3);
-            }
-            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            *reinterpret_cast<float4 *>(crow + col0 + j) = v;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (col < n) {
-              float v = __uint_as_float(r[j]);
-              if (bias) v += __ldg(bias + col);
-              if (relu) v = fmaxf(v, 0.f);
-              crow[col] = v;
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              if (col < n) {
+                float v = __uint_as_float(r[j]);
+                if (bias) v += __ldg(bias + col);
+                if (relu) v = fmaxf(v, 0.f);
+                crow[col] = v;
+              }
             }
           }
         }
       }
+      // this warp is done reading the accumulator buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-    }  // nkb > 0
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * ACC_COLS);
 }
 
 template <int NSPLIT, int BN, int STAGES, bool FP16, bool MN = false>
@@ -283,7 +321,6 @@ int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_b
     ksplit = (int)((2 * 148 + tiles - 1) / tiles);
     if (ksplit > nkb_total / 8) ksplit = nkb_total / 8;
     if (ksplit < 1) ksplit = 1;
-    if ((long long)batch * ksplit > 65535) ksplit = 1;
   }
   if (ksplit > 1) {
     cudaError_t ez = cudaSuccess;
@@ -299,8 +336,17 @@ int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_b
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const dim3 grid((m + BM - 1) / BM, (n + BN - 1) / BN, batch * ksplit);
-  kern<<<grid, 256, smem, s>>>(maps, m, n, kpad, b_batched, ksplit, bias, relu, out_half, c_out, ldc, c_batch_stride);
+  const long long nwork = tiles * ksplit;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const unsigned grid = (unsigned)(nwork < num_sms ? nwork : num_sms);
+  kern<<<grid, 256, smem, s>>>(maps, m, n, kpad, b_batched, ksplit, batch, bias, relu, out_half, c_out, ldc,
+                               c_batch_stride);
   return launch_status();
 }
 
