@@ -237,29 +237,43 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
             // fp16 output (CLIP ViT path), optional QuickGELU x * sigmoid(1.702 x)
             __half *hrow = reinterpret_cast<__half *>(c_void) + (size_t)batch * c_batch_stride + (size_t)row * ldc;
             const bool full = col0 + 32 <= n && (ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(hrow + col0) & 15) == 0);
+            if (full) {
 #pragma unroll
-            for (int j0 = 0; j0 < 32; j0 += 8) {
-              float v[8];
+              for (int j0 = 0; j0 < 32; j0 += 8) {
+                float v[8];
 #pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                const int col = col0 + j0 + t;
-                float x = __uint_as_float(r[j0 + t]);
-                if (bias && col < n) x += __ldg(bias + col);
-                if (act == 1) x = fmaxf(x, 0.f);
-                if (act == 2) x = x / (1.0f + __expf(-1.702f * x));
-                v[t] = x;
-              }
-              if (full) {  // 8 halves = one 16-byte store
+                for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[j0 + t]);
+                if (bias) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + col0 + j0));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + col0 + j0 + 4));
+                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                }
+                if (act == 1) {
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.f);
+                } else if (act == 2) {
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) v[t] = __fdividef(v[t], 1.0f + __expf(-1.702f * v[t]));
+                }
                 uint4 pk;
                 __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
                 __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
                 pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
                 pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
-                *reinterpret_cast<uint4 *>(hrow + col0 + j0) = pk;
-              } else {
-#pragma unroll
-                for (int t = 0; t < 8; ++t)
-                  if (col0 + j0 + t < n) hrow[col0 + j0 + t] = __float2half_rn(v[t]);
+                *reinterpret_cast<uint4 *>(hrow + col0 + j0) = pk;   // 8 halves = one 16-byte store
+              }
+            } else {
+#pragma unroll 4
+              for (int t = 0; t < 32; ++t) {
+                const int col = col0 + t;
+                if (col < n) {
+                  float x = __uint_as_float(r[t]);
+                  if (bias) x += __ldg(bias + col);
+                  if (act == 1) x = fmaxf(x, 0.f);
+                  if (act == 2) x = __fdividef(x, 1.0f + __expf(-1.702f * x));
+                  hrow[col] = __float2half_rn(x);
+                }
               }
             }
           } else if (ksplit > 1) {
