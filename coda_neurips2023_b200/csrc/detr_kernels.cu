@@ -2,6 +2,7 @@
 // B200 (sm_100a): LayerNorm fwd/bwd, row softmax, fused Fourier positional
 // encoding, generalised 3-D IoU with rotated-rectangle clipping, and a
 // warp-per-scene Hungarian solver.  C-ABI in include/coda_detr.h.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "../../include/coda_detr.h"
@@ -70,6 +71,50 @@ layer_norm_fwd_kernel(long long rows, float eps, const float *__restrict__ x,
   if (lane == 0) {
     if (mean_out) mean_out[row] = mean;
     if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+// fp16 activations (CLIP towers): same statistics in fp32, half in / half out
+template <int NV>  // c == NV * 128
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layer_norm_fwd_half_kernel(long long rows, float eps, const __half *__restrict__ x,
+                           const float *__restrict__ gamma, const float *__restrict__ beta,
+                           __half *__restrict__ y) {
+  constexpr int C = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint2 *xr = reinterpret_cast<const uint2 *>(x + row * C);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const uint2 raw = __ldg(xr + lane + i * 32);
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+    v[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + eps);
+  uint2 *yr = reinterpret_cast<uint2 *>(y + row * C);
+  const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
+  const float4 *b4 = reinterpret_cast<const float4 *>(beta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(g4 + lane + i * 32), b = __ldg(b4 + lane + i * 32);
+    const __half2 lo = __floats2half2_rn((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+    const __half2 hi = __floats2half2_rn((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const unsigned *>(&lo);
+    o.y = *reinterpret_cast<const unsigned *>(&hi);
+    yr[lane + i * 32] = o;
   }
 }
 
@@ -529,6 +574,24 @@ int coda_layer_norm_fwd(long long rows, int c, float eps, const float *x, const 
   cudaStream_t s = (cudaStream_t)stream;
 #define CODA_LN_FWD(NV) \
   case NV: layer_norm_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, s>>>(rows, eps, x, gamma, beta, y, mean, rstd); break;
+  switch (c / 128) {
+    CODA_LN_FWD(1) CODA_LN_FWD(2) CODA_LN_FWD(3) CODA_LN_FWD(4)
+    CODA_LN_FWD(5) CODA_LN_FWD(6) CODA_LN_FWD(7) CODA_LN_FWD(8)
+  }
+#undef CODA_LN_FWD
+  return launch_status();
+}
+
+int coda_layer_norm_fwd_half(long long rows, int c, float eps, const void *x, const float *gamma,
+                             const float *beta, void *y, void *stream) {
+  if (rows < 0 || c <= 0 || c % 128 != 0 || c > 1024) return CODA_EINVAL;
+  if (rows == 0) return CODA_OK;
+  if (!x || !gamma || !beta || !y) return CODA_EINVAL;
+  const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
+  cudaStream_t s = (cudaStream_t)stream;
+#define CODA_LN_FWD(NV) \
+  case NV: layer_norm_fwd_half_kernel<NV><<<grid, LN_WARPS * 32, 0, s>>>( \
+      rows, eps, (const __half *)x, gamma, beta, (__half *)y); break;
   switch (c / 128) {
     CODA_LN_FWD(1) CODA_LN_FWD(2) CODA_LN_FWD(3) CODA_LN_FWD(4)
     CODA_LN_FWD(5) CODA_LN_FWD(6) CODA_LN_FWD(7) CODA_LN_FWD(8)

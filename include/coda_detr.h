@@ -26,6 +26,15 @@ int coda_layer_norm_fwd(long long rows, int c, float eps, const float *x,
                         const float *gamma, const float *beta, float *y,
                         float *mean, float *rstd, void *stream);
 /*
+ * Forward-only variant for fp16 activations: x, y are IEEE half (rows, c); gamma,
+ * beta fp32; statistics in fp32 and one rounding to half at the end.
+ *   replaces the fp32-upcasting LayerNorm of the CLIP towers
+ *   (CLIP/clip/model.py:254-260: `super().forward(x.type(torch.float32)).type(orig_type)`)
+ */
+int coda_layer_norm_fwd_half(long long rows, int c, float eps, const void *x,
+                             const float *gamma, const float *beta, void *y,
+                             void *stream);
+/*
  *   dx (rows, c) may alias dy.  dgamma / dbeta (c) are fully written.
  *   `partial` is caller-provided scratch of coda_layer_norm_bwd_scratch(rows, c)
  *   floats (block partial sums, reduced deterministically).

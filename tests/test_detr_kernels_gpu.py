@@ -34,6 +34,21 @@ def test_layer_norm_fwd_bwd(rows, c):
     torch.testing.assert_close(gb, rb, rtol=1e-4, atol=1e-3 * max(1.0, rows ** 0.5 / 30))
 
 
+@pytest.mark.parametrize("rows,c", [(50 * 77, 768), (13, 512), (1, 128)])
+def test_layer_norm_half_matches_fp32_upcast(rows, c):
+    # CLIP's LayerNorm (CLIP/clip/model.py:254-260) = fp32 layer_norm of the fp16 input, rounded to fp16
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(rows, c, generator=g) * 2 + 0.3).half().cuda()
+    w = (torch.rand(c, generator=g) + 0.5).cuda()
+    b = torch.randn(c, generator=g).cuda()
+    y = ops.layer_norm_half(x, w, b, 1e-5)
+    ref = torch.nn.functional.layer_norm(x.float(), (c,), w, b, 1e-5).half()
+    assert y.dtype == torch.float16 and y.shape == x.shape
+    # same fp32 arithmetic up to summation order: at most one fp16 ulp apart
+    diff = (y.float() - ref.float()).abs()
+    assert (diff <= ref.float().abs() * 2 ** -10 + 1e-6).all()
+
+
 def test_layer_norm_module_matches_nn_layernorm_3d():
     ln = ops.LayerNorm(256).cuda()
     ref = torch.nn.LayerNorm(256).cuda()
