@@ -189,7 +189,8 @@ def attention_roofline(a, device):
                                      stream), "attention_pack")
 
     def launch():
-        return L.coda_attention_fwd_packed(b, h, lq, lk, hd, ns, P(ws), P(out), P(lse), ctypes.c_float(0.0), 0,
+        # dropout 0.1 as in the training step (enc_dropout): the mask is generated inside the kernel
+        return L.coda_attention_fwd_packed(b, h, lq, lk, hd, ns, P(ws), P(out), P(lse), ctypes.c_float(0.1), 12345,
                                            None, stream)
 
     for _ in range(3):
@@ -205,7 +206,7 @@ def attention_roofline(a, device):
     ms = e0.elapsed_time(e1) / reps
     flops = 4.0 * b * h * lq * lk * hd          # algorithmic: QK^T + PV, 2 flops per MAC
     achieved = flops / (ms * 1e-3) / 1e12
-    nprod = {1: 1, 2: 3, 3: 6}[ns]
+    nprod = {1: 1.0, 2: 3.0, 3: 5.5}[ns]       # QK^T: 1 / 3 / 6 plane products, PV: 1 / 3 / 5 (P carries 2 planes)
     return {"bound": "tensor", "kernel": "attn_fwd_kernel<64,%d> (tcgen05 fused encoder self-attention forward, "
             "L=2048, 4 heads x 64, batch %d)" % (ns, b),
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -213,7 +214,7 @@ def attention_roofline(a, device):
             "flops_per_launch": flops, "ms_per_launch": ms, "traffic": None,
             "tensor_pipe_flops_per_launch": flops * nprod,
             "tensor_pipe_frac": achieved * nprod / peak,
-            "note": "fp32 operands are split into %d bf16 planes, the tensor pipe executes %d bf16 MMAs per "
+            "note": "fp32 operands are split into %d bf16 planes, the tensor pipe executes %.1f bf16 MMAs per "
                     "algorithmic MMA; `achieved`/`frac` count algorithmic FLOPs only" % (ns, nprod)}
 
 

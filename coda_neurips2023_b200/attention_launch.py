@@ -62,14 +62,15 @@ def dropout_keep(bh: int, lq: int, lk: int, dropout_p: float, salt: int, device)
     ib = torch.arange(bh, device=device, dtype=torch.int64).view(bh, 1, 1)
     iq = torch.arange(lq, device=device, dtype=torch.int64).view(1, lq, 1)
     ik = torch.arange(lk, device=device, dtype=torch.int64).view(1, 1, lk)
-    h = (seed + ib * 0x9E3779B1 + iq * 0x85EBCA77 + ik * 0xC2B2AE3D) & M
+    h = (seed + ib * 0x9E3779B1 + iq * 0x85EBCA77 + (ik >> 1) * 0xC2B2AE3D) & M   # one hash per key pair
     h = h ^ (h >> 15)
     h = (h * 0x2C1B3C6D) & M
     h = h ^ (h >> 12)
     h = (h * 0x297A2D39) & M
     h = h ^ (h >> 15)
-    thresh = int(np.float32(dropout_p) * np.float32(16777216.0))
-    return (h & 0xFFFFFF) >= thresh
+    bits = torch.where((ik & 1) == 1, h >> 16, h & 0xFFFF)
+    thresh = int(np.float32(dropout_p) * np.float32(65536.0))
+    return bits >= thresh
 
 
 def dropout_mult(bh: int, lq: int, lk: int, dropout_p: float, salt: int, device) -> torch.Tensor:

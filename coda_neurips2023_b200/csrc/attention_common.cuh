@@ -11,6 +11,7 @@ namespace attn {
 constexpr int QT = 128;   // queries per CTA
 constexpr int KT = 64;    // keys per tile (one 128-byte swizzle span of bf16)
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
 
 __host__ __device__ constexpr int a_nprod(int ns) { return ns == 1 ? 1 : (ns == 2 ? 3 : 6); }
 __host__ __device__ constexpr int a_pa(int ns, int p) {
@@ -40,10 +41,18 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
   h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
   return h;
 }
-// keep-decision of element (bh, q, k); identical formula in attention_launch.py for the backward
-__device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t bh, uint32_t q, uint32_t k, uint32_t thresh24) {
-  const uint32_t h = mix32(seed + bh * 0x9E3779B1u + q * 0x85EBCA77u + k * 0xC2B2AE3Du);
-  return (h & 0xFFFFFFu) >= thresh24;
+// keep-decision of element (bh, q, k): one hash per (q, key pair), 16 bits per key;
+// identical formula in attention_launch.py (dropout_keep) for the reference twin
+__host__ __device__ __forceinline__ uint32_t drop_thresh16(float drop_p) { return (uint32_t)(drop_p * 65536.0f); }
+__device__ __forceinline__ uint32_t drop_row_base(uint32_t seed, uint32_t bh, uint32_t q) {
+  return seed + bh * 0x9E3779B1u + q * 0x85EBCA77u;
+}
+__device__ __forceinline__ uint32_t drop_pair_bits(uint32_t row_base, uint32_t kpair) {
+  return mix32(row_base + kpair * 0xC2B2AE3Du);
+}
+__device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t bh, uint32_t q, uint32_t k, uint32_t thresh16) {
+  const uint32_t h = drop_pair_bits(drop_row_base(seed, bh, q), k >> 1);
+  return ((k & 1u) ? (h >> 16) : (h & 0xFFFFu)) >= thresh16;
 }
 
 

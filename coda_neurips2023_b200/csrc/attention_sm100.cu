@@ -6,14 +6,19 @@
 // Numerics: q (pre-scaled), k, v are fp32; each is split into NSPLIT bf16 planes
 // (x = p0 + p1 (+ p2)) by attn_pack_kernel and the 1 / 3 / 6 significant cross
 // products are accumulated in fp32 -- fp32-class results at bf16 tensor-core rate
-// (same scheme as gemm_sm100.cu).  P (in [0, 1]) is split the same way.
+// (same scheme as gemm_sm100.cu).  P (in [0, 1]) carries at most two planes.  q is
+// packed with scale * log2(e), so the scores are in log2 units and the softmax is one
+// ex2 per element; the log-sum-exp is returned in natural-log units.
 //
 // One CTA = one (batch*head, 128-query tile); loop over 64-key tiles:
-//   warp 0 lane 0 : TMA producer (Q once; K_j, V^T_j per tile)
-//   warp 1 lane 0 : MMA issuer   S_j = Q K_j^T  -> TMEM[0,64);  O_j = P_j V_j -> TMEM[64, 64+HD)
+//   warp 0 lane 0 : TMA producer (Q once; K_j, V^T_j per tile, double-buffered for head dim 64)
+//   warp 1 lane 0 : MMA issuer   S_j = Q K_j^T -> TMEM[64 (j&1), +64) (double-buffered: S_{j+1} is
+//                   queued before O_j);  O_j = P_j V_j -> TMEM[128 + HD (j % NWG), +HD)
 //   warp 2        : TMEM alloc / dealloc
-//   warps 4..7    : softmax (thread = query row = TMEM lane): tcgen05.ld S_j, running max /
-//                   sum, P_j planes -> swizzled smem, then o = o * alpha + O_j from TMEM.
+//   warps 4..     : softmax (thread = query row = TMEM lane): tcgen05.ld S_j, running max / sum,
+//                   P_j planes -> swizzled smem, then o = o * alpha + O_j from TMEM.  Head dim 64
+//                   runs two such warpgroups on alternate key tiles (one works on its exponentials
+//                   while the tensor pipe serves the other) and merges their states at the end.
 #include <math.h>
 
 #include "../../include/coda_attention.h"
@@ -64,14 +69,14 @@ attn_pack_vt_kernel(int L, int Lpad, int B, int H, int HD, const float *__restri
 // materialised keep-mask * 1/(1-p) for the interim (cuBLAS) backward: mult[bh][q][k] in {0, 1/(1-p)}
 __global__ void __launch_bounds__(256)
 dropout_mult_kernel(long long total, int lq, int lk, uint32_t seed, const uint32_t *__restrict__ seed_dev,
-                    uint32_t thresh24, float keep_scale, float *__restrict__ mult) {
+                    uint32_t thresh16, float keep_scale, float *__restrict__ mult) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   if (seed_dev) seed += __ldg(seed_dev);
   const uint32_t k = (uint32_t)(i % lk);
   const long long t = i / lk;
   const uint32_t q = (uint32_t)(t % lq), bh = (uint32_t)(t / lq);
-  mult[i] = drop_keep(seed, bh, q, k, thresh24) ? keep_scale : 0.f;
+  mult[i] = drop_keep(seed, bh, q, k, thresh16) ? keep_scale : 0.f;
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -79,53 +84,87 @@ struct AttnMaps {
   CUtensorMap q[3], k[3], v[3];
 };
 
+// P lies in [0, 1] and is consumed once: two bf16 planes (relative error 2^-18) are enough even when
+// q, k, v carry three, which drops one of the six cross products of O = P V and a third of the
+// conversion work in the softmax warps.
+__host__ __device__ constexpr int p_planes(int ns) { return ns == 3 ? 2 : ns; }
+__host__ __device__ constexpr int pv_nprod(int ns) { return ns == 1 ? 1 : (ns == 2 ? 3 : 5); }
+__host__ __device__ constexpr int pv_pa(int ns, int p) {  // plane of P, smallest terms first
+  return ns == 1 ? 0 : ns == 2 ? (p == 0 ? 1 : 0) : (p == 0 ? 1 : p == 1 ? 0 : p == 2 ? 1 : 0);
+}
+__host__ __device__ constexpr int pv_pb(int ns, int p) {  // plane of V
+  return ns == 1 ? 0 : ns == 2 ? (p == 1 ? 1 : 0) : (p == 0 ? 1 : p == 1 ? 2 : p == 2 ? 0 : p == 3 ? 1 : 0);
+}
+
 template <int HD, int NSPLIT>
 struct AttnSmem {
+  // head dim 64: two softmax warpgroups take alternate key tiles (each with its own P / O buffers and its
+  // own running max / sum, merged at the end), K and V are double-buffered.  head dim 128: one warpgroup
+  // (the O accumulator of a row already fills its register budget) and single K / V stages.
+  static constexpr int NWG = HD == 64 ? 2 : 1;
+  static constexpr int NP = p_planes(NSPLIT);
   static constexpr int KB = HD / 64;                       // 64-wide k-blocks of the head dim
   static constexpr int Q_PLANE = QT * HD * 2;              // KB blocks of [128 x 64]
   static constexpr int K_PLANE = KT * HD * 2;              // KB blocks of [64 x 64]
   static constexpr int V_PLANE = HD * KT * 2;              // [HD x 64]
   static constexpr int P_PLANE = QT * KT * 2;              // [128 x 64]
-  static constexpr bool P_ALIASES_K = (NSPLIT * (Q_PLANE + K_PLANE + V_PLANE + P_PLANE) > 220 * 1024);
+  static constexpr int K_STAGE = NSPLIT * K_PLANE;
+  static constexpr int V_STAGE = NSPLIT * V_PLANE;
+  static constexpr int P_STAGE = NP * P_PLANE;
   static constexpr int Q_OFF = 0;
   static constexpr int K_OFF = NSPLIT * Q_PLANE;
-  static constexpr int V_OFF = K_OFF + NSPLIT * (K_PLANE > P_PLANE || !P_ALIASES_K ? K_PLANE : P_PLANE);
-  static constexpr int P_OFF = P_ALIASES_K ? K_OFF : V_OFF + NSPLIT * V_PLANE;
-  static constexpr int TOTAL = (P_ALIASES_K ? V_OFF + NSPLIT * V_PLANE : P_OFF + NSPLIT * P_PLANE);
+  static constexpr int V_OFF = K_OFF + NWG * K_STAGE;
+  static constexpr int P_OFF = V_OFF + NWG * V_STAGE;
+  static constexpr int TOTAL = P_OFF + NWG * P_STAGE;
+  static constexpr int THREADS = 128 + NWG * 128;
+  static_assert(NWG * (K_STAGE + V_STAGE) >= QT * 64 * 4 || NWG == 1, "merge scratch must fit in the K/V stages");
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int HD, int NSPLIT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(AttnSmem<HD, NSPLIT>::THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, int H, float *__restrict__ out,
                 float *__restrict__ lse, float drop_p, uint32_t seed, const uint32_t *__restrict__ seed_dev) {
   using SM = AttnSmem<HD, NSPLIT>;
   if (seed_dev) seed += __ldg(seed_dev);  // per-step counter kept on the device (CUDA-graph friendly)
-  constexpr int KB = SM::KB;
+  constexpr int KB = SM::KB, NWG = SM::NWG, NP = SM::NP;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t q_full, k_full, k_empty, v_full, v_empty, s_full, p_full, o_full;
+  __shared__ __align__(8) uint64_t q_full, k_full[NWG], k_empty[NWG], v_full[NWG], v_empty[NWG], s_full[2],
+      p_full[NWG], o_full[NWG];
   __shared__ uint32_t tmem_slot;
+  __shared__ float merge_ml[NWG == 2 ? QT : 1][2];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * QT, bh = blockIdx.y;
   const int ntiles = (Lk + KT - 1) / KT;
-  constexpr uint32_t TMEM_COLS = (64 + HD) <= 128 ? 128 : 256;
+  constexpr uint32_t TMEM_COLS = 256;  // S: 2 x 64 columns, O: NWG x HD columns
 
   if (warp == 0 && lane == 0) {
 #pragma unroll
     for (int p = 0; p < NSPLIT; ++p) { prefetch_tmap(&maps.q[p]); prefetch_tmap(&maps.k[p]); prefetch_tmap(&maps.v[p]); }
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(&q_full, 1); mbar_init(&k_full, 1); mbar_init(&k_empty, 1); mbar_init(&v_full, 1);
-    mbar_init(&v_empty, 1); mbar_init(&s_full, 1); mbar_init(&p_full, 128); mbar_init(&o_full, 1);
+    mbar_init(&q_full, 1);
+#pragma unroll
+    for (int i = 0; i < NWG; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1);
+    }
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
     mbar_fence_init_cluster();
   }
   if (warp == 2) tmem_alloc(&tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_s = tmem_slot;       // S_j : columns [0, 64)
-  const uint32_t tmem_o = tmem_slot + 64;  // O_j : columns [64, 64 + HD)
+  const uint32_t tmem_s = tmem_slot;        // S_j : columns [64 (j&1), +64)
+  const uint32_t tmem_o = tmem_slot + 128;  // O_j : columns [128 + HD (j % NWG), +HD)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -137,145 +176,184 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
         for (int kb = 0; kb < KB; ++kb)
           tma_load_3d(smem + SM::Q_OFF + p * SM::Q_PLANE + kb * (QT * 128), &maps.q[p], &q_full, kb * 64, q0, bh);
       for (int j = 0; j < ntiles; ++j) {
-        const uint32_t ph = (uint32_t)j & 1u;
-        mbar_wait(&k_empty, ph ^ 1u);
-        if (SM::P_ALIASES_K && j > 0) mbar_wait(&v_empty, ph ^ 1u);  // P_{j-1} (in K's buffer) consumed
-        mbar_arrive_expect_tx(&k_full, (uint32_t)(NSPLIT * SM::K_PLANE));
+        const int st = j % NWG;
+        const uint32_t ph = (uint32_t)(j / NWG) & 1u;
+        mbar_wait(&k_empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&k_full[st], (uint32_t)SM::K_STAGE);
 #pragma unroll
         for (int p = 0; p < NSPLIT; ++p)
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb)
-            tma_load_3d(smem + SM::K_OFF + p * SM::K_PLANE + kb * (KT * 128), &maps.k[p], &k_full, kb * 64, j * KT, bh);
-        mbar_wait(&v_empty, ph ^ 1u);
-        mbar_arrive_expect_tx(&v_full, (uint32_t)(NSPLIT * SM::V_PLANE));
+            tma_load_3d(smem + SM::K_OFF + st * SM::K_STAGE + p * SM::K_PLANE + kb * (KT * 128), &maps.k[p],
+                        &k_full[st], kb * 64, j * KT, bh);
+        mbar_wait(&v_empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&v_full[st], (uint32_t)SM::V_STAGE);
 #pragma unroll
         for (int p = 0; p < NSPLIT; ++p)
-          tma_load_3d(smem + SM::V_OFF + p * SM::V_PLANE, &maps.v[p], &v_full, j * KT, 0, bh);
+          tma_load_3d(smem + SM::V_OFF + st * SM::V_STAGE + p * SM::V_PLANE, &maps.v[p], &v_full[st], j * KT, 0, bh);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===== MMA issuer =====
+      // ===== MMA issuer: S_{j+1} = Q K_{j+1}^T is queued before O_j = P_j V_j so the tensor pipe works
+      //       on the next scores while the softmax warps are busy with the current ones =====
       constexpr uint32_t idesc_s = umma_idesc_f16(0, QT, KT);  // 128 x 64
       constexpr uint32_t idesc_o = umma_idesc_f16(0, QT, HD);  // 128 x HD
-      mbar_wait(&q_full, 0);
-      for (int j = 0; j < ntiles; ++j) {
-        const uint32_t ph = (uint32_t)j & 1u;
-        mbar_wait(&k_full, ph);
+      auto issue_s = [&](int j) {
+        const int st = j % NWG;
+        mbar_wait(&k_full[st], (uint32_t)(j / NWG) & 1u);
         tc_fence_after();
+        const uint32_t d = tmem_s + (uint32_t)(j & 1) * 64u;
 #pragma unroll
         for (int p = 0; p < a_nprod(NSPLIT); ++p)
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
             const uint64_t ad = umma_smem_desc_k_sw128(smem + SM::Q_OFF + a_pa(NSPLIT, p) * SM::Q_PLANE + kb * (QT * 128));
-            const uint64_t bd = umma_smem_desc_k_sw128(smem + SM::K_OFF + a_pb(NSPLIT, p) * SM::K_PLANE + kb * (KT * 128));
+            const uint64_t bd = umma_smem_desc_k_sw128(smem + SM::K_OFF + st * SM::K_STAGE +
+                                                       a_pb(NSPLIT, p) * SM::K_PLANE + kb * (KT * 128));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_f16(tmem_s, umma_desc_advance(ad, kk * 32), umma_desc_advance(bd, kk * 32), idesc_s,
+              umma_f16(d, umma_desc_advance(ad, kk * 32), umma_desc_advance(bd, kk * 32), idesc_s,
                        (uint32_t)((p | kb | kk) != 0));
           }
-        if (!SM::P_ALIASES_K) umma_commit(&k_empty);
-        umma_commit(&s_full);
-        mbar_wait(&p_full, ph);
-        mbar_wait(&v_full, ph);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(&q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % NWG;
+        const uint32_t ph = (uint32_t)(j / NWG) & 1u;
+        // the S buffer of tile j+1 held tile j-1, whose p_full was awaited one iteration ago
+        if (j + 1 < ntiles) issue_s(j + 1);
+        mbar_wait(&p_full[st], ph);
+        mbar_wait(&v_full[st], ph);
         tc_fence_after();
+        const uint32_t d = tmem_o + (uint32_t)st * HD;
 #pragma unroll
-        for (int p = 0; p < a_nprod(NSPLIT); ++p) {
-          const uint64_t ad = umma_smem_desc_k_sw128(smem + SM::P_OFF + a_pa(NSPLIT, p) * SM::P_PLANE);
-          const uint64_t bd = umma_smem_desc_k_sw128(smem + SM::V_OFF + a_pb(NSPLIT, p) * SM::V_PLANE);
+        for (int p = 0; p < pv_nprod(NSPLIT); ++p) {
+          const uint64_t ad = umma_smem_desc_k_sw128(smem + SM::P_OFF + st * SM::P_STAGE + pv_pa(NSPLIT, p) * SM::P_PLANE);
+          const uint64_t bd = umma_smem_desc_k_sw128(smem + SM::V_OFF + st * SM::V_STAGE + pv_pb(NSPLIT, p) * SM::V_PLANE);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_f16(tmem_o, umma_desc_advance(ad, kk * 32), umma_desc_advance(bd, kk * 32), idesc_o,
+            umma_f16(d, umma_desc_advance(ad, kk * 32), umma_desc_advance(bd, kk * 32), idesc_o,
                      (uint32_t)((p | kk) != 0));
         }
-        if (SM::P_ALIASES_K) umma_commit(&k_empty);
-        umma_commit(&v_empty);
-        umma_commit(&o_full);
+        umma_commit(&v_empty[st]);
+        umma_commit(&o_full[st]);
       }
     }
   } else if (warp >= 4) {
-    // ===== softmax / accumulation: one thread per query row =====
-    const int q = warp - 4;
+    // ===== softmax / accumulation: one thread per query row; warpgroup g owns tiles j = g (mod NWG) =====
+    const int g = (warp - 4) >> 2;
+    const int q = (warp - 4) & 3;
     const int row = q * 32 + lane;             // row in the tile == TMEM lane
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float o_acc[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
+    // scores arrive in log2 units (q was packed with scale * log2 e): p = 2^(s - m)
     float m_run = -INFINITY, l_run = 0.f;
     const bool dropout = drop_p > 0.f;
-    const uint32_t thresh24 = (uint32_t)(drop_p * 16777216.0f);
+    const uint32_t thresh16 = drop_thresh16(drop_p);
     const float keep_scale = dropout ? 1.0f / (1.0f - drop_p) : 1.0f;
-    unsigned char *prow = smem + SM::P_OFF + row * 128;
+    const uint32_t drop_base = drop_row_base(seed, (uint32_t)bh, (uint32_t)(q0 + row));
+    unsigned char *prow = smem + SM::P_OFF + g * SM::P_STAGE + row * 128;
+    const uint32_t my_o = tmem_o + (uint32_t)g * HD + lane_base;
 
-    for (int j = 0; j < ntiles; ++j) {
-      const uint32_t ph = (uint32_t)j & 1u;
-      mbar_wait(&s_full, ph);
+    for (int j = g; j < ntiles; j += NWG) {
+      const uint32_t ph = (uint32_t)(j / NWG) & 1u;
+      mbar_wait(&s_full[j & 1], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       uint32_t sr[2][32];
-      tmem_ld_32x32(tmem_s + lane_base, sr[0]);
-      tmem_ld_32x32(tmem_s + lane_base + 32, sr[1]);
+      tmem_ld_32x32(tmem_s + (uint32_t)(j & 1) * 64u + lane_base, sr[0]);
+      tmem_ld_32x32(tmem_s + (uint32_t)(j & 1) * 64u + lane_base + 32, sr[1]);
       tmem_ld_wait();
-      const int kvalid = Lk - j * KT;  // keys >= kvalid are padding
-      float mloc = -INFINITY;
+      const int kvalid = Lk - j * KT;  // keys >= kvalid are padding (last tile only)
+      if (kvalid < KT) {
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float s = __uint_as_float(sr[c >> 5][c & 31]);
-        if (c >= kvalid) s = -INFINITY;
-        sr[c >> 5][c & 31] = __float_as_uint(s);
-        mloc = fmaxf(mloc, s);
+        for (int c = 0; c < 64; ++c)
+          if (c >= kvalid) sr[c >> 5][c & 31] = __float_as_uint(-INFINITY);
       }
+      float mloc = __uint_as_float(sr[0][0]);
+#pragma unroll
+      for (int c = 1; c < 64; ++c) mloc = fmaxf(mloc, __uint_as_float(sr[c >> 5][c & 31]));
       const float m_new = fmaxf(m_run, mloc);
-      const float alpha = exp2f((m_run - m_new) * LOG2E);  // m_run = -inf on the first tile -> 0
+      const float alpha = ex2_approx(m_run - m_new);  // m_run = -inf on the first tile -> 0
       float lsum = 0.f;
-      // P_j -> NSPLIT bf16 planes, K-major 128B-swizzled rows of 64 keys
+      // P_j -> NP bf16 planes, K-major 128B-swizzled rows of 64 keys
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
-        uint32_t w[3][4];
+        uint32_t w[NP][4];
 #pragma unroll
         for (int e = 0; e < 8; e += 2) {
-          float pv[2];
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int c = ch * 8 + e + t;
-            float p = exp2f((__uint_as_float(sr[c >> 5][c & 31]) - m_new) * LOG2E);
-            lsum += p;
-            if (dropout) p = drop_keep(seed, (uint32_t)bh, (uint32_t)(q0 + row), (uint32_t)(j * KT + c), thresh24) ? p * keep_scale : 0.f;
-            pv[t] = p;
+          const int c = ch * 8 + e;
+          float r0 = ex2_approx(__uint_as_float(sr[c >> 5][c & 31]) - m_new);
+          float r1 = ex2_approx(__uint_as_float(sr[(c + 1) >> 5][(c + 1) & 31]) - m_new);
+          lsum += r0 + r1;
+          if (dropout) {
+            const uint32_t hbits = drop_pair_bits(drop_base, (uint32_t)(j * (KT / 2) + (c >> 1)));
+            r0 = (hbits & 0xFFFFu) >= thresh16 ? r0 * keep_scale : 0.f;
+            r1 = (hbits >> 16) >= thresh16 ? r1 * keep_scale : 0.f;
           }
-          float r0 = pv[0], r1 = pv[1];
 #pragma unroll
-          for (int pl = 0; pl < NSPLIT; ++pl) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(r0), h1 = __float2bfloat16_rn(r1);
-            w[pl][e >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            r0 -= __bfloat162float(h0);
-            r1 -= __bfloat162float(h1);
+          for (int pl = 0; pl < NP; ++pl) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(r0, r1);  // one packed conversion
+            const uint32_t bits = *reinterpret_cast<const uint32_t *>(&h2);
+            w[pl][e >> 1] = bits;
+            if (pl + 1 < NP) {
+              r0 -= __uint_as_float(bits << 16);
+              r1 -= __uint_as_float(bits & 0xFFFF0000u);
+            }
           }
         }
         const uint32_t off = (uint32_t)((ch ^ (row & 7)) << 4);
 #pragma unroll
-        for (int pl = 0; pl < NSPLIT; ++pl)
+        for (int pl = 0; pl < NP; ++pl)
           *reinterpret_cast<uint4 *>(prow + pl * SM::P_PLANE + off) = make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
       }
       l_run = l_run * alpha + lsum;
       m_run = m_new;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P visible to the tensor core (async proxy)
       tc_fence_before();
-      mbar_arrive(&p_full);
+      mbar_arrive(&p_full[g]);
       // O_j = P_j V_j, then o = o * alpha + O_j
-      mbar_wait(&o_full, ph);
+      mbar_wait(&o_full[g], ph);
       tc_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < HD; c0 += 32) {
         uint32_t orr[32];
-        tmem_ld_32x32(tmem_o + lane_base + c0, orr);
+        tmem_ld_32x32(my_o + c0, orr);
         tmem_ld_wait();
 #pragma unroll
         for (int t = 0; t < 32; ++t) o_acc[c0 + t] = o_acc[c0 + t] * alpha + __uint_as_float(orr[t]);
       }
     }
-    // ===== epilogue: normalise, store (Lq, B, H*HD) and the log-sum-exp =====
+    if (NWG == 2) {
+      // ===== merge the two warpgroups' partial softmax states (disjoint key subsets) =====
+      // every tile's o_full has been awaited by its owner, so after this barrier no MMA reads smem any more
+      float *scratch = reinterpret_cast<float *>(smem + SM::K_OFF);  // [HD][128] floats, row fastest
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (g == 1) {
+#pragma unroll
+        for (int d = 0; d < HD; ++d) scratch[d * QT + row] = o_acc[d];
+        merge_ml[row][0] = m_run;
+        merge_ml[row][1] = l_run;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (g == 0) {
+        const float m1 = merge_ml[row][0], l1 = merge_ml[row][1];
+        const float m = fmaxf(m_run, m1);            // warpgroup 0 owns tile 0: m_run is finite
+        const float a0 = ex2_approx(m_run - m), a1 = ex2_approx(m1 - m);
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o_acc[d] = o_acc[d] * a0 + scratch[d * QT + row] * a1;
+        l_run = l_run * a0 + l1 * a1;
+        m_run = m;
+      }
+    }
+    // ===== epilogue: normalise, store (Lq, B, H*HD) and the log-sum-exp (natural-log units) =====
     const int qrow = q0 + row;
-    if (qrow < Lq) {
+    if (g == 0 && qrow < Lq) {
       const float inv = 1.0f / l_run;
       const int b = bh / H, h = bh - b * H;
       float *orow = out + ((size_t)qrow * B + b) * (size_t)(H * HD) + (size_t)h * HD;
@@ -283,7 +361,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
       for (int d = 0; d < HD; d += 4)
         *reinterpret_cast<float4 *>(orow + d) =
             make_float4(o_acc[d] * inv, o_acc[d + 1] * inv, o_acc[d + 2] * inv, o_acc[d + 3] * inv);
-      if (lse) lse[(size_t)bh * Lq + qrow] = m_run + logf(l_run);
+      if (lse) lse[(size_t)bh * Lq + qrow] = m_run * LN2 + logf(l_run);
     }
   }
   tc_fence_before();
@@ -294,7 +372,8 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
 template <int HD, int NSPLIT>
 int launch_attn(const AttnMaps &maps, int Lq, int Lk, int B, int H, float *out, float *lse, float drop_p,
                 uint32_t seed, const uint32_t *seed_dev, cudaStream_t s) {
-  constexpr size_t smem = AttnSmem<HD, NSPLIT>::TOTAL + 1024;
+  using SM = AttnSmem<HD, NSPLIT>;
+  constexpr size_t smem = SM::TOTAL + 1024;
   auto kern = attn_fwd_kernel<HD, NSPLIT>;
   static bool configured = false;  // once per template instance
   if (!configured) {
@@ -303,7 +382,7 @@ int launch_attn(const AttnMaps &maps, int Lq, int Lk, int B, int H, float *out, 
     configured = true;
   }
   const dim3 grid((Lq + QT - 1) / QT, B * H);
-  kern<<<grid, 256, smem, s>>>(maps, Lq, Lk, B, H, out, lse, drop_p, seed, seed_dev);
+  kern<<<grid, SM::THREADS, smem, s>>>(maps, Lq, Lk, B, H, out, lse, drop_p, seed, seed_dev);
   return launch_status();
 }
 
@@ -337,7 +416,7 @@ int coda_attention_pack(int b, int h, int lq, int lk, int hd, int nsplit, float 
   const long long tq = (long long)lq * bh * hd, tk = (long long)lk * bh * hd;
   const dim3 gvp((lkpad + 31) / 32, (hd + 31) / 32, bh);
 #define CODA_PACK(NS)                                                                                          \
-  attn_pack_rows_kernel<NS><<<(unsigned)((tq + 255) / 256), 256, 0, s>>>(lq, b, h, hd, scale, q, qp);           \
+  attn_pack_rows_kernel<NS><<<(unsigned)((tq + 255) / 256), 256, 0, s>>>(lq, b, h, hd, scale * LOG2E, q, qp);           \
   attn_pack_rows_kernel<NS><<<(unsigned)((tk + 255) / 256), 256, 0, s>>>(lk, b, h, hd, 1.0f, k, kp);            \
   attn_pack_vt_kernel<NS><<<gvp, 256, 0, s>>>(lk, lkpad, b, h, hd, v, vp);
   if (nsplit == 1) { CODA_PACK(1) } else if (nsplit == 2) { CODA_PACK(2) } else { CODA_PACK(3) }
@@ -387,7 +466,7 @@ int coda_attention_dropout_mult(int bh, int lq, int lk, float dropout_p, unsigne
   if (total == 0) return CODA_OK;
   if (!mult) return CODA_EINVAL;
   dropout_mult_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      total, lq, lk, seed, seed_dev, (uint32_t)(dropout_p * 16777216.0f), 1.0f / (1.0f - dropout_p), mult);
+      total, lq, lk, seed, seed_dev, drop_thresh16(dropout_p), 1.0f / (1.0f - dropout_p), mult);
   return launch_status();
 }
 
