@@ -11,7 +11,8 @@
 // ex2 per element; the log-sum-exp is returned in natural-log units.
 //
 // One CTA = one (batch*head, 128-query tile); loop over 64-key tiles:
-//   warp 0 lane 0 : TMA producer (Q once; K_j, V^T_j per tile, double-buffered for head dim 64)
+//   warp 0 lane 0 : TMA producer of Q (once) and K_j;  warp 3 lane 0 : TMA producer of V^T_j
+//                   (K / V double-buffered for head dim 64)
 //   warp 1 lane 0 : MMA issuer   S_j = Q K_j^T -> TMEM[64 (j&1), +64) (double-buffered: S_{j+1} is
 //                   queued before O_j);  O_j = P_j V_j -> TMEM[128 + HD (j % NWG), +HD)
 //   warp 2        : TMEM alloc / dealloc
@@ -136,7 +137,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t q_full, k_full[NWG], k_empty[NWG], v_full[NWG], v_empty[NWG], s_full[2],
-      p_full[NWG], o_full[NWG];
+      s_free[2], p_full[NWG], o_full[NWG];
   __shared__ uint32_t tmem_slot;
   __shared__ float merge_ml[NWG == 2 ? QT : 1][2];
 
@@ -157,6 +158,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
       mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1);
     }
     mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    mbar_init(&s_free[0], 128); mbar_init(&s_free[1], 128);
     mbar_fence_init_cluster();
   }
   if (warp == 2) tmem_alloc(&tmem_slot, TMEM_COLS);
@@ -186,6 +188,14 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
           for (int kb = 0; kb < KB; ++kb)
             tma_load_3d(smem + SM::K_OFF + st * SM::K_STAGE + p * SM::K_PLANE + kb * (KT * 128), &maps.k[p],
                         &k_full[st], kb * 64, j * KT, bh);
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ===== TMA producer of V^T_j (own thread: a K load never queues behind a V stage still in use) =====
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % NWG;
+        const uint32_t ph = (uint32_t)(j / NWG) & 1u;
         mbar_wait(&v_empty[st], ph ^ 1u);
         mbar_arrive_expect_tx(&v_full[st], (uint32_t)SM::V_STAGE);
 #pragma unroll
@@ -195,8 +205,8 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===== MMA issuer: S_{j+1} = Q K_{j+1}^T is queued before O_j = P_j V_j so the tensor pipe works
-      //       on the next scores while the softmax warps are busy with the current ones =====
+      // ===== MMA issuer: the scores run two tiles ahead of O_j = P_j V_j so the tensor pipe works on the
+      //       next scores while the softmax warps are busy with the current ones =====
       constexpr uint32_t idesc_s = umma_idesc_f16(0, QT, KT);  // 128 x 64
       constexpr uint32_t idesc_o = umma_idesc_f16(0, QT, HD);  // 128 x HD
       auto issue_s = [&](int j) {
@@ -221,11 +231,19 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
       };
       mbar_wait(&q_full, 0);
       issue_s(0);
+      if (ntiles > 1) issue_s(1);
+      // scores two tiles ahead: their TMEM buffer is free once the softmax warps hold S_j in registers
+      // (s_free, long before p_full), so S_{j+2} is ready when its warpgroup finishes tile j
+      auto ahead = [&](int j) {
+        if (j + 2 < ntiles) {
+          mbar_wait(&s_free[j & 1], (uint32_t)(j >> 1) & 1u);
+          issue_s(j + 2);
+        }
+      };
       for (int j = 0; j < ntiles; ++j) {
         const int st = j % NWG;
         const uint32_t ph = (uint32_t)(j / NWG) & 1u;
-        // the S buffer of tile j+1 held tile j-1, whose p_full was awaited one iteration ago
-        if (j + 1 < ntiles) issue_s(j + 1);
+        ahead(j);
         mbar_wait(&p_full[st], ph);
         mbar_wait(&v_full[st], ph);
         tc_fence_after();
@@ -269,6 +287,8 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
       tmem_ld_32x32(tmem_s + (uint32_t)(j & 1) * 64u + lane_base, sr[0]);
       tmem_ld_32x32(tmem_s + (uint32_t)(j & 1) * 64u + lane_base + 32, sr[1]);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[j & 1]);     // S_j is in registers: its TMEM buffer may take S_{j+2}
       const int kvalid = Lk - j * KT;  // keys >= kvalid are padding (last tile only)
       if (kvalid < KT) {
 #pragma unroll
@@ -293,8 +313,8 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
           lsum += r0 + r1;
           if (dropout) {
             const uint32_t hbits = drop_pair_bits(drop_base, (uint32_t)(j * (KT / 2) + (c >> 1)));
-            r0 = (hbits & 0xFFFFu) >= thresh16 ? r0 * keep_scale : 0.f;
-            r1 = (hbits >> 16) >= thresh16 ? r1 * keep_scale : 0.f;
+            r0 = (hbits & 0xFFFFu) >= thresh16 ? r0 : 0.f;   // the 1/(1-p) factor is applied once, at the end
+            r1 = (hbits >> 16) >= thresh16 ? r1 : 0.f;
           }
 #pragma unroll
           for (int pl = 0; pl < NP; ++pl) {
@@ -354,7 +374,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
     // ===== epilogue: normalise, store (Lq, B, H*HD) and the log-sum-exp (natural-log units) =====
     const int qrow = q0 + row;
     if (g == 0 && qrow < Lq) {
-      const float inv = 1.0f / l_run;
+      const float inv = keep_scale / l_run;
       const int b = bh / H, h = bh - b * H;
       float *orow = out + ((size_t)qrow * B + b) * (size_t)(H * HD) + (size_t)h * HD;
 #pragma unroll
