@@ -55,22 +55,41 @@ def forward(q, k, v, nhead: int, dropout_p: float = 0.0, salt: int = 0, nsplit: 
     return out, lse
 
 
+_LCG_A, _LCG_C = 747796405, 2891336453
+
+
+def _lcg_jump():
+    """(a[c], c[c]) with x_c = a[c] * s + c[c] (mod 2^32): the LCG stepped c + 1 times (attention_common.cuh)."""
+    M = 0xFFFFFFFF
+    a, c, ja, jc = _LCG_A, _LCG_C, [], []
+    for _ in range(64):
+        ja.append(a)
+        jc.append(c)
+        c = (c * _LCG_A + _LCG_C) & M
+        a = (a * _LCG_A) & M
+    return ja, jc
+
+
 def dropout_keep(bh: int, lq: int, lk: int, dropout_p: float, salt: int, device) -> torch.Tensor:
-    """(bh, lq, lk) bool keep-mask, bit-identical to drop_keep() in csrc/attention_sm100.cu."""
+    """(bh, lq, lk) bool keep-mask, bit-identical to drop_keep() in csrc/attention_common.cuh."""
     M = 0xFFFFFFFF
     seed = (seed_counter(device).to(torch.int64) & M) + (salt & M)   # stays on the device: no sync
     ib = torch.arange(bh, device=device, dtype=torch.int64).view(bh, 1, 1)
     iq = torch.arange(lq, device=device, dtype=torch.int64).view(1, lq, 1)
     ik = torch.arange(lk, device=device, dtype=torch.int64).view(1, 1, lk)
-    h = (seed + ib * 0x9E3779B1 + iq * 0x85EBCA77 + (ik >> 1) * 0xC2B2AE3D) & M   # one hash per key pair
+    h = (seed + ib * 0x9E3779B1 + iq * 0x85EBCA77 + (ik >> 6) * 0xC2B2AE3D) & M   # one hash per 64-key tile
     h = h ^ (h >> 15)
     h = (h * 0x2C1B3C6D) & M
     h = h ^ (h >> 12)
     h = (h * 0x297A2D39) & M
     h = h ^ (h >> 15)
-    bits = torch.where((ik & 1) == 1, h >> 16, h & 0xFFFF)
-    thresh = int(np.float32(dropout_p) * np.float32(65536.0))
-    return bits >= thresh
+    ja, jc = _lcg_jump()
+    ja = torch.tensor(ja, dtype=torch.int64, device=device)[ik & 63]
+    jc = torch.tensor(jc, dtype=torch.int64, device=device)[ik & 63]
+    # 32 x 32 -> low 32 bits without overflowing int64: split the multiplier
+    x = ((h * (ja & 0xFFFF)) + (((h * (ja >> 16)) & 0xFFFF) << 16) + jc) & M
+    thresh = int(float(np.float32(dropout_p)) * 4294967296.0)
+    return x >= thresh
 
 
 def dropout_mult(bh: int, lq: int, lk: int, dropout_p: float, salt: int, device) -> torch.Tensor:

@@ -203,7 +203,7 @@ attn_bwd_dq_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B, 
     const float lse_r = valid_row ? __ldg(lse + (size_t)bh * Lq + qrow) : 0.f;
     const float d_r = valid_row ? __ldg(delta + (size_t)bh * Lq + qrow) : 0.f;
     const bool dropout = drop_p > 0.f;
-    const uint32_t thresh16 = drop_thresh16(drop_p);
+    const uint32_t thresh32 = drop_thresh32(drop_p);
     const float keep_scale = dropout ? 1.0f / (1.0f - drop_p) : 1.0f;
     for (int j = 0; j < ntiles; ++j) {
       const uint32_t ph = (uint32_t)j & 1u;
@@ -224,7 +224,7 @@ attn_bwd_dq_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B, 
         const float s = __uint_as_float(sr[c >> 5][c & 31]);
         float p = (c < kvalid && valid_row) ? exp2f((s - lse_r) * LOG2E) : 0.f;
         float dp = __uint_as_float(pr[c >> 5][c & 31]);
-        if (dropout) dp = drop_keep(seed, (uint32_t)bh, (uint32_t)qrow, (uint32_t)(j * 64 + c), thresh16) ? dp * keep_scale : 0.f;
+        if (dropout) dp = drop_keep(seed, (uint32_t)bh, (uint32_t)qrow, (uint32_t)(j * 64 + c), thresh32) ? dp * keep_scale : 0.f;
         ds[c] = p * (dp - d_r);
       }
       store_row_planes(smem + SM::DS_OFF, SM::T128, row, ds);
@@ -368,7 +368,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B,
     const int krow = k0 + row;
     const bool valid_row = krow < Lk;
     const bool dropout = drop_p > 0.f;
-    const uint32_t thresh16 = drop_thresh16(drop_p);
+    const uint32_t thresh32 = drop_thresh32(drop_p);
     const float keep_scale = dropout ? 1.0f / (1.0f - drop_p) : 1.0f;
     for (int i = 0; i < ntiles; ++i) {
       const uint32_t ph = (uint32_t)i & 1u;
@@ -398,7 +398,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B,
         const float p = (c < qvalid && valid_row) ? exp2f((s - s_lse[i & 1][c]) * LOG2E) : 0.f;
         float dp = __uint_as_float(pr[c >> 5][c & 31]);
         float m = 1.0f;
-        if (dropout) m = drop_keep(seed, (uint32_t)bh, (uint32_t)(i * 64 + c), (uint32_t)krow, thresh16) ? keep_scale : 0.f;
+        if (dropout) m = drop_keep(seed, (uint32_t)bh, (uint32_t)(i * 64 + c), (uint32_t)krow, thresh32) ? keep_scale : 0.f;
         pt[c] = p * m;
         ds[c] = p * (dp * m - s_delta[i & 1][c]);
       }

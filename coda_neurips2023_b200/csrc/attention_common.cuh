@@ -41,18 +41,36 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
   h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
   return h;
 }
-// keep-decision of element (bh, q, k): one hash per (q, key pair), 16 bits per key;
-// identical formula in attention_launch.py (dropout_keep) for the reference twin
-__host__ __device__ __forceinline__ uint32_t drop_thresh16(float drop_p) { return (uint32_t)(drop_p * 65536.0f); }
-__device__ __forceinline__ uint32_t drop_row_base(uint32_t seed, uint32_t bh, uint32_t q) {
-  return seed + bh * 0x9E3779B1u + q * 0x85EBCA77u;
+// keep-decision of element (bh, q, k).  One strong hash per (row, 64-key tile) seeds a 32-bit LCG that is
+// stepped along the keys (x_c = A^(c+1) s + C (A^c + ... + 1), available in closed form for any c), and an
+// element is kept when x_c >= p * 2^32.  The forward kernel walks the sequence with one IMAD per element;
+// attention_launch.py (dropout_keep) restates the same formula for the reference twin.
+constexpr uint32_t LCG_A = 747796405u, LCG_C = 2891336453u;
+struct LcgJump {
+  uint32_t a[KT], c[KT];
+};
+__host__ __device__ constexpr LcgJump make_lcg_jump() {
+  LcgJump t{};
+  uint32_t a = LCG_A, c = LCG_C;
+  for (int i = 0; i < KT; ++i) {
+    t.a[i] = a;
+    t.c[i] = c;
+    c = c * LCG_A + LCG_C;
+    a = a * LCG_A;
+  }
+  return t;
 }
-__device__ __forceinline__ uint32_t drop_pair_bits(uint32_t row_base, uint32_t kpair) {
-  return mix32(row_base + kpair * 0xC2B2AE3Du);
+static __constant__ LcgJump kLcgJump = make_lcg_jump();
+
+__host__ __device__ __forceinline__ uint32_t drop_thresh32(float drop_p) {
+  return (uint32_t)((double)drop_p * 4294967296.0);
 }
-__device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t bh, uint32_t q, uint32_t k, uint32_t thresh16) {
-  const uint32_t h = drop_pair_bits(drop_row_base(seed, bh, q), k >> 1);
-  return ((k & 1u) ? (h >> 16) : (h & 0xFFFFu)) >= thresh16;
+__device__ __forceinline__ uint32_t drop_tile_seed(uint32_t seed, uint32_t bh, uint32_t q, uint32_t tile) {
+  return mix32(seed + bh * 0x9E3779B1u + q * 0x85EBCA77u + tile * 0xC2B2AE3Du);
+}
+__device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t bh, uint32_t q, uint32_t k, uint32_t thresh32) {
+  const uint32_t s = drop_tile_seed(seed, bh, q, k / KT);
+  return s * kLcgJump.a[k % KT] + kLcgJump.c[k % KT] >= thresh32;
 }
 
 

@@ -70,19 +70,19 @@ attn_pack_vt_kernel(int L, int Lpad, int B, int H, int HD, const float *__restri
 // materialised keep-mask * 1/(1-p) for the interim (cuBLAS) backward: mult[bh][q][k] in {0, 1/(1-p)}
 __global__ void __launch_bounds__(256)
 dropout_mult_kernel(long long total, int lq, int lk, uint32_t seed, const uint32_t *__restrict__ seed_dev,
-                    uint32_t thresh16, float keep_scale, float *__restrict__ mult) {
+                    uint32_t thresh32, float keep_scale, float *__restrict__ mult) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   if (seed_dev) seed += __ldg(seed_dev);
   const uint32_t k = (uint32_t)(i % lk);
   const long long t = i / lk;
   const uint32_t q = (uint32_t)(t % lq), bh = (uint32_t)(t / lq);
-  mult[i] = drop_keep(seed, bh, q, k, thresh16) ? keep_scale : 0.f;
+  mult[i] = drop_keep(seed, bh, q, k, thresh32) ? keep_scale : 0.f;
 }
 
 // ------------------------------------------------------------------ the kernel
 struct AttnMaps {
-  CUtensorMap q[3], k[3], v[3];
+  CUtensorMap k[3], v[3];
 };
 
 // P lies in [0, 1] and is consumed once: two bf16 planes (relative error 2^-18) are enough even when
@@ -97,28 +97,36 @@ __host__ __device__ constexpr int pv_pb(int ns, int p) {  // plane of V
   return ns == 1 ? 0 : ns == 2 ? (p == 1 ? 1 : 0) : (p == 0 ? 1 : p == 1 ? 2 : p == 2 ? 0 : p == 3 ? 1 : 0);
 }
 
+// The A operands of both contractions live in TMEM (tcgen05.mma with [a_tmem]): the Q planes are written
+// there once per CTA, the P planes by the softmax warps every tile.  Only K and V^T (the B operands) are
+// read from shared memory, which takes the 4 KB A-tile read per MMA off the shared-memory port -- with
+// eleven plane products per key tile that port, not the tensor pipe, was the limiter.
 template <int HD, int NSPLIT>
-struct AttnSmem {
+struct AttnCfg {
   // head dim 64: two softmax warpgroups take alternate key tiles (each with its own P / O buffers and its
-  // own running max / sum, merged at the end), K and V are double-buffered.  head dim 128: one warpgroup
-  // (the O accumulator of a row already fills its register budget) and single K / V stages.
+  // own running max / sum, merged at the end).  head dim 128: one warpgroup (the O accumulator of a row
+  // already fills its register budget).
   static constexpr int NWG = HD == 64 ? 2 : 1;
+  static constexpr int NST = HD == 64 ? 4 : 2;             // K / V^T stages
   static constexpr int NP = p_planes(NSPLIT);
   static constexpr int KB = HD / 64;                       // 64-wide k-blocks of the head dim
-  static constexpr int Q_PLANE = QT * HD * 2;              // KB blocks of [128 x 64]
   static constexpr int K_PLANE = KT * HD * 2;              // KB blocks of [64 x 64]
   static constexpr int V_PLANE = HD * KT * 2;              // [HD x 64]
-  static constexpr int P_PLANE = QT * KT * 2;              // [128 x 64]
   static constexpr int K_STAGE = NSPLIT * K_PLANE;
   static constexpr int V_STAGE = NSPLIT * V_PLANE;
-  static constexpr int P_STAGE = NP * P_PLANE;
-  static constexpr int Q_OFF = 0;
-  static constexpr int K_OFF = NSPLIT * Q_PLANE;
-  static constexpr int V_OFF = K_OFF + NWG * K_STAGE;
-  static constexpr int P_OFF = V_OFF + NWG * V_STAGE;
-  static constexpr int TOTAL = P_OFF + NWG * P_STAGE;
+  static constexpr int K_OFF = 0;
+  static constexpr int V_OFF = NST * K_STAGE;
+  static constexpr int TOTAL = NST * (K_STAGE + V_STAGE);
   static constexpr int THREADS = 128 + NWG * 128;
-  static_assert(NWG * (K_STAGE + V_STAGE) >= QT * 64 * 4 || NWG == 1, "merge scratch must fit in the K/V stages");
+  // TMEM columns (32-bit): S double buffer | O per warpgroup | P planes per warpgroup | Q planes
+  static constexpr int S_COL = 0;
+  static constexpr int O_COL = 128;
+  static constexpr int P_COL = O_COL + NWG * HD;
+  static constexpr int P_COLS = NP * (KT / 2);             // bf16 pairs: 32 columns per plane
+  static constexpr int Q_COL = P_COL + NWG * P_COLS;
+  static constexpr int Q_COLS = HD / 2;                    // per plane
+  static_assert(Q_COL + NSPLIT * Q_COLS <= 512, "TMEM budget");
+  static_assert(NWG == 1 || TOTAL >= QT * 64 * 4, "merge scratch must fit in the K/V stages");
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -128,15 +136,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <int HD, int NSPLIT>
-__global__ void __launch_bounds__(AttnSmem<HD, NSPLIT>::THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, int H, float *__restrict__ out,
-                float *__restrict__ lse, float drop_p, uint32_t seed, const uint32_t *__restrict__ seed_dev) {
-  using SM = AttnSmem<HD, NSPLIT>;
+__global__ void __launch_bounds__(AttnCfg<HD, NSPLIT>::THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__restrict__ qplanes, int Lq, int Lk,
+                int B, int H, float *__restrict__ out, float *__restrict__ lse, float drop_p, uint32_t seed,
+                const uint32_t *__restrict__ seed_dev) {
+  using SM = AttnCfg<HD, NSPLIT>;
   if (seed_dev) seed += __ldg(seed_dev);  // per-step counter kept on the device (CUDA-graph friendly)
-  constexpr int KB = SM::KB, NWG = SM::NWG, NP = SM::NP;
+  constexpr int KB = SM::KB, NWG = SM::NWG, NP = SM::NP, NST = SM::NST;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t q_full, k_full[NWG], k_empty[NWG], v_full[NWG], v_empty[NWG], s_full[2],
+  __shared__ __align__(8) uint64_t q_full, k_full[NST], k_empty[NST], v_full[NST], v_empty[NST], s_full[2],
       s_free[2], p_full[NWG], o_full[NWG];
   __shared__ uint32_t tmem_slot;
   __shared__ float merge_ml[NWG == 2 ? QT : 1][2];
@@ -144,19 +153,20 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * QT, bh = blockIdx.y;
   const int ntiles = (Lk + KT - 1) / KT;
-  constexpr uint32_t TMEM_COLS = 256;  // S: 2 x 64 columns, O: NWG x HD columns
+  constexpr uint32_t TMEM_COLS = 512;
 
   if (warp == 0 && lane == 0) {
 #pragma unroll
-    for (int p = 0; p < NSPLIT; ++p) { prefetch_tmap(&maps.q[p]); prefetch_tmap(&maps.k[p]); prefetch_tmap(&maps.v[p]); }
+    for (int p = 0; p < NSPLIT; ++p) { prefetch_tmap(&maps.k[p]); prefetch_tmap(&maps.v[p]); }
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(&q_full, 1);
+    mbar_init(&q_full, 128);
 #pragma unroll
-    for (int i = 0; i < NWG; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1);
     }
+#pragma unroll
+    for (int i = 0; i < NWG; ++i) { mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); }
     mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
     mbar_init(&s_free[0], 128); mbar_init(&s_free[1], 128);
     mbar_fence_init_cluster();
@@ -165,22 +175,17 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_s = tmem_slot;        // S_j : columns [64 (j&1), +64)
-  const uint32_t tmem_o = tmem_slot + 128;  // O_j : columns [128 + HD (j % NWG), +HD)
+  const uint32_t tmem_s = tmem_slot + SM::S_COL;  // S_j : columns [64 (j&1), +64)
+  const uint32_t tmem_o = tmem_slot + SM::O_COL;  // O_j : columns [HD (j % NWG), +HD)
+  const uint32_t tmem_p = tmem_slot + SM::P_COL;  // P_j planes of warpgroup j % NWG (bf16 pairs)
+  const uint32_t tmem_q = tmem_slot + SM::Q_COL;  // Q planes (bf16 pairs), written once
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
-      mbar_arrive_expect_tx(&q_full, (uint32_t)(NSPLIT * SM::Q_PLANE));
-#pragma unroll
-      for (int p = 0; p < NSPLIT; ++p)
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_3d(smem + SM::Q_OFF + p * SM::Q_PLANE + kb * (QT * 128), &maps.q[p], &q_full, kb * 64, q0, bh);
+      // ===== TMA producer of K_j =====
       for (int j = 0; j < ntiles; ++j) {
-        const int st = j % NWG;
-        const uint32_t ph = (uint32_t)(j / NWG) & 1u;
-        mbar_wait(&k_empty[st], ph ^ 1u);
+        const int st = j % NST;
+        mbar_wait(&k_empty[st], ((uint32_t)(j / NST) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&k_full[st], (uint32_t)SM::K_STAGE);
 #pragma unroll
         for (int p = 0; p < NSPLIT; ++p)
@@ -194,9 +199,8 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
     if (lane == 0) {
       // ===== TMA producer of V^T_j (own thread: a K load never queues behind a V stage still in use) =====
       for (int j = 0; j < ntiles; ++j) {
-        const int st = j % NWG;
-        const uint32_t ph = (uint32_t)(j / NWG) & 1u;
-        mbar_wait(&v_empty[st], ph ^ 1u);
+        const int st = j % NST;
+        mbar_wait(&v_empty[st], ((uint32_t)(j / NST) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&v_full[st], (uint32_t)SM::V_STAGE);
 #pragma unroll
         for (int p = 0; p < NSPLIT; ++p)
@@ -204,62 +208,62 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer: the scores run two tiles ahead of O_j = P_j V_j so the tensor pipe works on the
-      //       next scores while the softmax warps are busy with the current ones =====
-      constexpr uint32_t idesc_s = umma_idesc_f16(0, QT, KT);  // 128 x 64
-      constexpr uint32_t idesc_o = umma_idesc_f16(0, QT, HD);  // 128 x HD
-      auto issue_s = [&](int j) {
-        const int st = j % NWG;
-        mbar_wait(&k_full[st], (uint32_t)(j / NWG) & 1u);
-        tc_fence_after();
+    // ===== MMA issuer (whole warp in uniform control flow, one elected lane issues): the scores run two
+    //       tiles ahead of O_j = P_j V_j so the tensor pipe works on the next scores while the softmax
+    //       warps are busy with the current ones =====
+    constexpr uint32_t idesc_s = umma_idesc_f16(0, QT, KT);  // 128 x 64
+    constexpr uint32_t idesc_o = umma_idesc_f16(0, QT, HD);  // 128 x HD
+    auto issue_s = [&](int j) {
+      const int st = j % NST;
+      mbar_wait(&k_full[st], (uint32_t)(j / NST) & 1u);
+      tc_fence_after();
+      if (elect_one_sync()) {
         const uint32_t d = tmem_s + (uint32_t)(j & 1) * 64u;
 #pragma unroll
         for (int p = 0; p < a_nprod(NSPLIT); ++p)
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
-            const uint64_t ad = umma_smem_desc_k_sw128(smem + SM::Q_OFF + a_pa(NSPLIT, p) * SM::Q_PLANE + kb * (QT * 128));
+            const uint32_t a = tmem_q + (uint32_t)(a_pa(NSPLIT, p) * SM::Q_COLS + kb * 32);
             const uint64_t bd = umma_smem_desc_k_sw128(smem + SM::K_OFF + st * SM::K_STAGE +
                                                        a_pb(NSPLIT, p) * SM::K_PLANE + kb * (KT * 128));
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_f16(d, umma_desc_advance(ad, kk * 32), umma_desc_advance(bd, kk * 32), idesc_s,
-                       (uint32_t)((p | kb | kk) != 0));
+            for (int kk = 0; kk < 4; ++kk)  // 16 head-dim elements = 8 TMEM columns per MMA
+              umma_f16_ts(d, a + kk * 8, umma_desc_advance(bd, kk * 32), idesc_s, (uint32_t)((p | kb | kk) != 0));
           }
         umma_commit(&k_empty[st]);
         umma_commit(&s_full[j & 1]);
-      };
-      mbar_wait(&q_full, 0);
-      issue_s(0);
-      if (ntiles > 1) issue_s(1);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&q_full, 0);
+    tc_fence_after();
+    issue_s(0);
+    if (ntiles > 1) issue_s(1);
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j % NST, g = j % NWG;
       // scores two tiles ahead: their TMEM buffer is free once the softmax warps hold S_j in registers
       // (s_free, long before p_full), so S_{j+2} is ready when its warpgroup finishes tile j
-      auto ahead = [&](int j) {
-        if (j + 2 < ntiles) {
-          mbar_wait(&s_free[j & 1], (uint32_t)(j >> 1) & 1u);
-          issue_s(j + 2);
-        }
-      };
-      for (int j = 0; j < ntiles; ++j) {
-        const int st = j % NWG;
-        const uint32_t ph = (uint32_t)(j / NWG) & 1u;
-        ahead(j);
-        mbar_wait(&p_full[st], ph);
-        mbar_wait(&v_full[st], ph);
-        tc_fence_after();
-        const uint32_t d = tmem_o + (uint32_t)st * HD;
+      if (j + 2 < ntiles) {
+        mbar_wait(&s_free[j & 1], (uint32_t)(j >> 1) & 1u);
+        issue_s(j + 2);
+      }
+      mbar_wait(&p_full[g], (uint32_t)(j / NWG) & 1u);
+      mbar_wait(&v_full[st], (uint32_t)(j / NST) & 1u);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t d = tmem_o + (uint32_t)g * HD;
 #pragma unroll
         for (int p = 0; p < pv_nprod(NSPLIT); ++p) {
-          const uint64_t ad = umma_smem_desc_k_sw128(smem + SM::P_OFF + st * SM::P_STAGE + pv_pa(NSPLIT, p) * SM::P_PLANE);
+          const uint32_t a = tmem_p + (uint32_t)(g * SM::P_COLS + pv_pa(NSPLIT, p) * (KT / 2));
           const uint64_t bd = umma_smem_desc_k_sw128(smem + SM::V_OFF + st * SM::V_STAGE + pv_pb(NSPLIT, p) * SM::V_PLANE);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_f16(d, umma_desc_advance(ad, kk * 32), umma_desc_advance(bd, kk * 32), idesc_o,
-                     (uint32_t)((p | kk) != 0));
+          for (int kk = 0; kk < 4; ++kk)   // 16 keys = 8 TMEM columns per MMA
+            umma_f16_ts(d, a + kk * 8, umma_desc_advance(bd, kk * 32), idesc_o, (uint32_t)((p | kk) != 0));
         }
         umma_commit(&v_empty[st]);
-        umma_commit(&o_full[st]);
+        umma_commit(&o_full[g]);
       }
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===== softmax / accumulation: one thread per query row; warpgroup g owns tiles j = g (mod NWG) =====
@@ -267,17 +271,37 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
     const int q = (warp - 4) & 3;
     const int row = q * 32 + lane;             // row in the tile == TMEM lane
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    if (g == 0) {
+      // Q planes of this row -> TMEM (A operand of every S_j): bf16 pairs, 16 elements per 8 columns
+      const bool valid = q0 + row < Lq;
+#pragma unroll
+      for (int p = 0; p < NSPLIT; ++p) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(
+            qplanes + (((size_t)p * gridDim.y + bh) * Lq + (valid ? q0 + row : 0)) * HD);
+#pragma unroll
+        for (int c = 0; c < HD / 16; ++c) {
+          const uint4 lo = valid ? __ldg(src + 2 * c) : make_uint4(0, 0, 0, 0);
+          const uint4 hi = valid ? __ldg(src + 2 * c + 1) : make_uint4(0, 0, 0, 0);
+          const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          tmem_st_32x8(tmem_q + lane_base + (uint32_t)(p * SM::Q_COLS + c * 8), w);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&q_full);
+    }
     float o_acc[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
     // scores arrive in log2 units (q was packed with scale * log2 e): p = 2^(s - m)
     float m_run = -INFINITY, l_run = 0.f;
     const bool dropout = drop_p > 0.f;
-    const uint32_t thresh16 = drop_thresh16(drop_p);
+    const uint32_t thresh32 = drop_thresh32(drop_p);
     const float keep_scale = dropout ? 1.0f / (1.0f - drop_p) : 1.0f;
-    const uint32_t drop_base = drop_row_base(seed, (uint32_t)bh, (uint32_t)(q0 + row));
-    unsigned char *prow = smem + SM::P_OFF + g * SM::P_STAGE + row * 128;
+    constexpr LcgJump jump = make_lcg_jump();  // four interleaved chains: x_{c+4} = x_c A^4 + C_4
+    const uint32_t lcg_a4 = jump.a[3], lcg_c4 = jump.c[3];
     const uint32_t my_o = tmem_o + (uint32_t)g * HD + lane_base;
+    const uint32_t my_p = tmem_p + (uint32_t)(g * SM::P_COLS) + lane_base;
 
     for (int j = g; j < ntiles; j += NWG) {
       const uint32_t ph = (uint32_t)(j / NWG) & 1u;
@@ -301,20 +325,27 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
       const float m_new = fmaxf(m_run, mloc);
       const float alpha = ex2_approx(m_run - m_new);  // m_run = -inf on the first tile -> 0
       float lsum = 0.f;
-      // P_j -> NP bf16 planes, K-major 128B-swizzled rows of 64 keys
+      uint32_t dx[4] = {0, 0, 0, 0};
+      if (dropout) {
+        const uint32_t ts = drop_tile_seed(seed, (uint32_t)bh, (uint32_t)(q0 + row), (uint32_t)j);
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        uint32_t w[NP][4];
+        for (int i = 0; i < 4; ++i) dx[i] = ts * jump.a[i] + jump.c[i];
+      }
+      // P_j -> NP bf16 planes in TMEM (A operand of O_j): 16 keys = 8 columns of bf16 pairs per store
 #pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-          const int c = ch * 8 + e;
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t w[NP][8];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          const int c = ch * 16 + e;
           float r0 = ex2_approx(__uint_as_float(sr[c >> 5][c & 31]) - m_new);
           float r1 = ex2_approx(__uint_as_float(sr[(c + 1) >> 5][(c + 1) & 31]) - m_new);
           lsum += r0 + r1;
           if (dropout) {
-            const uint32_t hbits = drop_pair_bits(drop_base, (uint32_t)(j * (KT / 2) + (c >> 1)));
-            r0 = (hbits & 0xFFFFu) >= thresh16 ? r0 : 0.f;   // the 1/(1-p) factor is applied once, at the end
-            r1 = (hbits >> 16) >= thresh16 ? r1 : 0.f;
+            r0 = dx[c & 3] >= thresh32 ? r0 : 0.f;   // the 1/(1-p) factor is applied once, at the end
+            r1 = dx[(c + 1) & 3] >= thresh32 ? r1 : 0.f;
+            dx[c & 3] = dx[c & 3] * lcg_a4 + lcg_c4;
+            dx[(c + 1) & 3] = dx[(c + 1) & 3] * lcg_a4 + lcg_c4;
           }
 #pragma unroll
           for (int pl = 0; pl < NP; ++pl) {
@@ -327,14 +358,12 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
             }
           }
         }
-        const uint32_t off = (uint32_t)((ch ^ (row & 7)) << 4);
 #pragma unroll
-        for (int pl = 0; pl < NP; ++pl)
-          *reinterpret_cast<uint4 *>(prow + pl * SM::P_PLANE + off) = make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
+        for (int pl = 0; pl < NP; ++pl) tmem_st_32x8(my_p + (uint32_t)(pl * (KT / 2) + ch * 8), w[pl]);
       }
       l_run = l_run * alpha + lsum;
       m_run = m_new;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P visible to the tensor core (async proxy)
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[g]);
       // O_j = P_j V_j, then o = o * alpha + O_j
@@ -352,7 +381,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
     if (NWG == 2) {
       // ===== merge the two warpgroups' partial softmax states (disjoint key subsets) =====
       // every tile's o_full has been awaited by its owner, so after this barrier no MMA reads smem any more
-      float *scratch = reinterpret_cast<float *>(smem + SM::K_OFF);  // [HD][128] floats, row fastest
+      float *scratch = reinterpret_cast<float *>(smem);  // [HD][128] floats, row fastest
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (g == 1) {
 #pragma unroll
@@ -390,9 +419,9 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, int Lq, int Lk, int B, in
 }
 
 template <int HD, int NSPLIT>
-int launch_attn(const AttnMaps &maps, int Lq, int Lk, int B, int H, float *out, float *lse, float drop_p,
-                uint32_t seed, const uint32_t *seed_dev, cudaStream_t s) {
-  using SM = AttnSmem<HD, NSPLIT>;
+int launch_attn(const AttnMaps &maps, const __nv_bfloat16 *qplanes, int Lq, int Lk, int B, int H, float *out,
+                float *lse, float drop_p, uint32_t seed, const uint32_t *seed_dev, cudaStream_t s) {
+  using SM = AttnCfg<HD, NSPLIT>;
   constexpr size_t smem = SM::TOTAL + 1024;
   auto kern = attn_fwd_kernel<HD, NSPLIT>;
   static bool configured = false;  // once per template instance
@@ -402,7 +431,7 @@ int launch_attn(const AttnMaps &maps, int Lq, int Lk, int B, int H, float *out, 
     configured = true;
   }
   const dim3 grid((Lq + QT - 1) / QT, B * H);
-  kern<<<grid, SM::THREADS, smem, s>>>(maps, Lq, Lk, B, H, out, lse, drop_p, seed, seed_dev);
+  kern<<<grid, SM::THREADS, smem, s>>>(maps, qplanes, Lq, Lk, B, H, out, lse, drop_p, seed, seed_dev);
   return launch_status();
 }
 
@@ -459,15 +488,13 @@ int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, 
   const __nv_bfloat16 *vp = kp + (size_t)nsplit * bh * lk * hd;
   AttnMaps maps;
   for (int p = 0; p < nsplit; ++p) {
-    st = make_tmap_k_major_16b(&maps.q[p], qp + (size_t)p * bh * lq * hd, 0, hd, lq, bh, hd, (long long)lq * hd, QT);
-    if (st != CODA_OK) return st;
     st = make_tmap_k_major_16b(&maps.k[p], kp + (size_t)p * bh * lk * hd, 0, hd, lk, bh, hd, (long long)lk * hd, KT);
     if (st != CODA_OK) return st;
     st = make_tmap_k_major_16b(&maps.v[p], vp + (size_t)p * bh * hd * lkpad, 0, lkpad, hd, bh, lkpad,
                                (long long)hd * lkpad, hd);
     if (st != CODA_OK) return st;
   }
-#define CODA_ATTN(HD_, NS) return launch_attn<HD_, NS>(maps, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s)
+#define CODA_ATTN(HD_, NS) return launch_attn<HD_, NS>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s)
   if (hd == 64) {
     if (nsplit == 1) CODA_ATTN(64, 1);
     if (nsplit == 2) CODA_ATTN(64, 2);
@@ -486,7 +513,7 @@ int coda_attention_dropout_mult(int bh, int lq, int lk, float dropout_p, unsigne
   if (total == 0) return CODA_OK;
   if (!mult) return CODA_EINVAL;
   dropout_mult_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      total, lq, lk, seed, seed_dev, drop_thresh16(dropout_p), 1.0f / (1.0f - dropout_p), mult);
+      total, lq, lk, seed, seed_dev, drop_thresh32(dropout_p), 1.0f / (1.0f - dropout_p), mult);
   return launch_status();
 }
 
