@@ -159,13 +159,14 @@ attn_bwd_dq_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B, 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(0, 128, 64);
-      mbar_wait(&q_full, 0);
-      for (int j = 0; j < ntiles; ++j) {
-        const uint32_t ph = (uint32_t)j & 1u;
-        mbar_wait(&kv_full, ph);
-        tc_fence_after();
+    // warp-uniform control flow, one elected lane issues (see elect_one_sync)
+    constexpr uint32_t idesc = umma_idesc_f16(0, 128, 64);
+    mbar_wait(&q_full, 0);
+    for (int j = 0; j < ntiles; ++j) {
+      const uint32_t ph = (uint32_t)j & 1u;
+      mbar_wait(&kv_full, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
 #pragma unroll
         for (int p = 0; p < NPROD; ++p) {
           const uint64_t aq = umma_smem_desc_k_sw128(smem + SM::Q_OFF + a_pa(NS, p) * SM::T128);
@@ -180,9 +181,12 @@ attn_bwd_dq_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B, 
         }
         umma_commit(&kv_empty);
         umma_commit(&s_full);
-        mbar_wait(&ds_full, ph);
-        mbar_wait(&kt_full, ph);
-        tc_fence_after();
+      }
+      __syncwarp();
+      mbar_wait(&ds_full, ph);
+      mbar_wait(&kt_full, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
 #pragma unroll
         for (int p = 0; p < NPROD; ++p) {
           const uint64_t as = umma_smem_desc_k_sw128(smem + SM::DS_OFF + a_pa(NS, p) * SM::T128);
@@ -192,8 +196,9 @@ attn_bwd_dq_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B, 
             umma_f16(tm_dq, umma_desc_advance(as, kk * 32), umma_desc_advance(bt, kk * 32), idesc, (uint32_t)((j | p | kk) != 0));
         }
         umma_commit(&kt_empty);  // also: dS_j consumed (next dS write waits on s_full of j+1, issued after this)
+        if (j == ntiles - 1) umma_commit(&dq_done);
       }
-      umma_commit(&dq_done);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int qq = warp - 4, row = qq * 32 + lane;
@@ -322,13 +327,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B,
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(0, 128, 64);
-      mbar_wait(&kv_full, 0);
-      for (int i = 0; i < ntiles; ++i) {
-        const uint32_t ph = (uint32_t)i & 1u;
-        mbar_wait(&q_full, ph);
-        tc_fence_after();
+    // warp-uniform control flow, one elected lane issues (see elect_one_sync)
+    constexpr uint32_t idesc = umma_idesc_f16(0, 128, 64);
+    mbar_wait(&kv_full, 0);
+    for (int i = 0; i < ntiles; ++i) {
+      const uint32_t ph = (uint32_t)i & 1u;
+      mbar_wait(&q_full, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
 #pragma unroll
         for (int p = 0; p < NPROD; ++p) {
           const uint64_t ak = umma_smem_desc_k_sw128(smem + SM::K_OFF + a_pa(NS, p) * SM::T128);
@@ -343,9 +349,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B,
         }
         umma_commit(&q_empty);
         umma_commit(&s_full);
-        mbar_wait(&p_full, ph);
-        mbar_wait(&t_full, ph);
-        tc_fence_after();
+      }
+      __syncwarp();
+      mbar_wait(&p_full, ph);
+      mbar_wait(&t_full, ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
 #pragma unroll
         for (int p = 0; p < NPROD; ++p) {
           const uint64_t ap = umma_smem_desc_k_sw128(smem + SM::P_OFF + a_pa(NS, p) * SM::T128);
@@ -359,8 +368,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B,
           }
         }
         umma_commit(&t_empty);  // Q^T/dO^T stage free, and P~^T / dS^T consumed
+        if (i == ntiles - 1) umma_commit(&acc_done);
       }
-      umma_commit(&acc_done);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int qq = warp - 4, row = qq * 32 + lane;  // key row

@@ -141,17 +141,17 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      uint32_t it = 0;  // running k-block counter across work items -> stage / phase
-      for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
-        int m0, n0, batch, ks;
-        decode(w, m0, n0, batch, ks);
-        const int kb0 = ks * per, nkb = max(0, min(per, nkb_total - kb0));
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
+    // ===== TMA producer (warp-uniform control flow; one elected lane issues the copies) =====
+    uint32_t it = 0;  // running k-block counter across work items -> stage / phase
+    for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+      int m0, n0, batch, ks;
+      decode(w, m0, n0, batch, ks);
+      const int kb0 = ks * per, nkb = max(0, min(per, nkb_total - kb0));
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[s], (uint32_t)STAGE);
           unsigned char *st = smem + (size_t)s * STAGE;
 #pragma unroll
@@ -172,27 +172,28 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
             }
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc_f16(FP16 ? 1 : 0, BM, BN, MN ? 1 : 0, MN ? 1 : 0);
-      uint32_t it = 0, tile_i = 0;
-      for (long long w = blockIdx.x; w < nwork; w += gridDim.x, ++tile_i) {
-        int m0, n0, batch, ks;
-        decode(w, m0, n0, batch, ks);
-        const int kb0 = ks * per, nkb = max(0, min(per, nkb_total - kb0));
-        if (nkb == 0) continue;  // (the epilogue skips it as well)
-        const uint32_t buf = tile_i & 1u, use = tile_i >> 1;
-        mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);  // epilogue drained this accumulator buffer
+    // ===== MMA issuer (warp-uniform control flow; one elected lane issues, see elect_one_sync) =====
+    constexpr uint32_t idesc = umma_idesc_f16(FP16 ? 1 : 0, BM, BN, MN ? 1 : 0, MN ? 1 : 0);
+    uint32_t it = 0, tile_i = 0;
+    for (long long w = blockIdx.x; w < nwork; w += gridDim.x, ++tile_i) {
+      int m0, n0, batch, ks;
+      decode(w, m0, n0, batch, ks);
+      const int kb0 = ks * per, nkb = max(0, min(per, nkb_total - kb0));
+      if (nkb == 0) continue;  // (the epilogue skips it as well)
+      const uint32_t buf = tile_i & 1u, use = tile_i >> 1;
+      mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);  // epilogue drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * ACC_COLS;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + buf * ACC_COLS;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
+        if (elect_one_sync()) {
           unsigned char *st = smem + (size_t)s * STAGE;
 #pragma unroll
           for (int p = 0; p < n_products(NSPLIT); ++p) {
@@ -206,8 +207,9 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
                        (uint32_t)((kb | p | kk) != 0));
           }
           umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          if (kb == nkb - 1) umma_commit(&acc_full[buf]);   // accumulator complete
         }
-        umma_commit(&acc_full[buf]);   // accumulator complete
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

@@ -10,10 +10,27 @@ sys.path.insert(0, str(ROOT))
 from coda_neurips2023_b200 import ops  # noqa: E402
 
 
-def timeit(fn, reps=20, warm=3):
+def timeit(fn, reps=20, warm=3, graph=True):
+    """Per-call device time.  With graph=True the calls are replayed from a CUDA graph, so the
+    host cost of a launch (ctypes, tensor-map encoding) is not part of the number -- as in the training step."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if graph:
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(reps):
+                    fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
@@ -43,9 +60,9 @@ for (m, n, k) in [(16384, 768, 256), (16384, 512, 512), (16384, 1024, 512), (819
     def fb():
         y = ops.linear(x, w)
         y.backward(y)
-    row["linear_fwd_bwd_ms"] = round(timeit(fb, reps=5), 4)
+    row["linear_fwd_bwd_ms"] = round(timeit(fb, reps=5, graph=False), 4)
     def fb_t():
         y = torch.nn.functional.linear(x, w)
         y.backward(y)
-    row["torch_linear_fwd_bwd_ms"] = round(timeit(fb_t, reps=5), 4)
+    row["torch_linear_fwd_bwd_ms"] = round(timeit(fb_t, reps=5, graph=False), 4)
     print(json.dumps(row), flush=True)
