@@ -105,16 +105,16 @@ def dropout_mult(bh: int, lq: int, lk: int, dropout_p: float, salt: int, device)
 
 
 def backward(q, k, v, out, dout, lse, nhead: int, dropout_p: float = 0.0, salt: int = 0):
-    """Fused tcgen05 backward (head dim 64): returns (dq, dk, dv), each shaped like its input."""
+    """Fused tcgen05 backward (head dim 64 / 128): returns (dq, dk, dv), each shaped like its input."""
     lq, b, e = q.shape
     lk = k.shape[0]
     hd = e // nhead
-    assert hd == 64
+    assert hd in (64, 128)
     q, k, v, out, dout = (t.contiguous() for t in (q, k, v, out, dout))
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
     L = lib()
     L.coda_attention_bwd_workspace_bytes.restype = ctypes.c_longlong
-    ws = torch.empty(int(L.coda_attention_bwd_workspace_bytes(b, nhead, lq, lk)), dtype=torch.uint8, device=q.device)
+    ws = torch.empty(int(L.coda_attention_bwd_workspace_bytes(b, nhead, lq, lk, hd)), dtype=torch.uint8, device=q.device)
     seed_dev = seed_counter(q.device) if dropout_p > 0.0 else None
     with torch.cuda.device(q.device):
         st = L.coda_attention_bwd(ctypes.c_int(b), ctypes.c_int(nhead), ctypes.c_int(lq), ctypes.c_int(lk),

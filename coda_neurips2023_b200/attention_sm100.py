@@ -54,19 +54,8 @@ class _Attention(torch.autograd.Function):
         from . import attention_launch
 
         q, k, v, out, lse = ctx.saved_tensors
-        if q.shape[-1] // ctx.nhead == 64:
-            # encoder head size: fused tcgen05 backward (dQ kernel + dK/dV kernel)
-            dq, dk, dv = attention_launch.backward(q, k, v, out, dout, lse, ctx.nhead, ctx.dropout_p, ctx.salt)
-            return dq, dk, dv, None, None, None
-        # head dim 128 (decoder, small Lq): re-derive P with cuBLAS batched GEMMs, same dropout mask
-        keep = None
-        if ctx.dropout_p > 0.0:
-            keep = attention_launch.dropout_mult(q.shape[1] * ctx.nhead, q.shape[0], k.shape[0], ctx.dropout_p,
-                                                 ctx.salt, q.device)
-        with torch.enable_grad():
-            qq, kk, vv = (t.detach().requires_grad_(True) for t in (q, k, v))
-            out = _math(qq, kk, vv, ctx.nhead, ctx.dropout_p, False, False, keep)
-        dq, dk, dv = torch.autograd.grad(out, (qq, kk, vv), dout)
+        # fused tcgen05 backward (dQ kernel + dK/dV kernel); P is recomputed tile by tile, never stored
+        dq, dk, dv = attention_launch.backward(q, k, v, out, dout, lse, ctx.nhead, ctx.dropout_p, ctx.salt)
         return dq, dk, dv, None, None, None
 
 

@@ -45,14 +45,14 @@ int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, 
                               const unsigned int *seed_dev, void *stream);
 
 /*
- * Backward of coda_attention_fwd for hd == 64 (the encoder's head size): two fused tcgen05 kernels
- * (dQ row-wise; dK, dV column-wise) that recompute the probabilities from `lse`, regenerate the
- * dropout mask from the same counter hash, and never write an (Lq x Lk) tensor.
- *   q, k, v, out, dout as in the forward ((l, b, h*64) fp32); lse (b*h, lq) from the forward;
- *   dq (lq, b, h*64), dk / dv (lk, b, h*64) fully written.  Operands are split into 2 bf16 planes.
- *   workspace: coda_attention_bwd_workspace_bytes(b, h, lq, lk) bytes.
+ * Backward of coda_attention_fwd (hd 64 or 128): two fused tcgen05 kernels (dQ row-wise; dK, dV
+ * column-wise) that recompute the probabilities from `lse`, regenerate the dropout mask from the same
+ * counter stream, and never write an (Lq x Lk) tensor.
+ *   q, k, v, out, dout as in the forward ((l, b, h*hd) fp32); lse (b*h, lq) from the forward;
+ *   dq (lq, b, h*hd), dk / dv (lk, b, h*hd) fully written.  Operands are split into 2 bf16 planes.
+ *   workspace: coda_attention_bwd_workspace_bytes(b, h, lq, lk, hd) bytes.
  */
-long long coda_attention_bwd_workspace_bytes(int b, int h, int lq, int lk);
+long long coda_attention_bwd_workspace_bytes(int b, int h, int lq, int lk, int hd);
 int coda_attention_bwd(int b, int h, int lq, int lk, int hd, float scale, const float *q, const float *k,
                        const float *v, const float *out, const float *dout, const float *lse, float *dq,
                        float *dk, float *dv, float dropout_p, unsigned int seed,

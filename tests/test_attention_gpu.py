@@ -71,11 +71,13 @@ def test_attention_autograd_wrapper():
     assert (outs.mean(0) - ref.detach()).abs().mean().item() < 0.05
 
 
-@pytest.mark.parametrize("lq,lk,b,h", [(128, 128, 1, 1), (2048, 2048, 1, 4), (300, 200, 2, 2), (64, 1000, 2, 4), (50, 50, 3, 12)])
+@pytest.mark.parametrize("lq,lk,b,h,hd", [
+    (128, 128, 1, 1, 64), (2048, 2048, 1, 4, 64), (300, 200, 2, 2, 64), (64, 1000, 2, 4, 64), (50, 50, 3, 12, 64),
+    (128, 64, 1, 1, 128), (256, 2048, 2, 4, 128), (256, 256, 2, 4, 128), (130, 200, 1, 2, 128), (3, 2, 1, 1, 128)])
 @pytest.mark.parametrize("p", [0.0, 0.1])
-def test_attention_backward_hd64_vs_fp64(lq, lk, b, h, p):
+def test_attention_backward_vs_fp64(lq, lk, b, h, hd, p):
     torch.manual_seed(lq + lk)
-    e = h * 64
+    e = h * hd
     q = (torch.randn(lq, b, e, device="cuda") * 1.2).requires_grad_(True)
     k = (torch.randn(lk, b, e, device="cuda") * 1.2).requires_grad_(True)
     v = torch.randn(lk, b, e, device="cuda", requires_grad=True)
