@@ -323,11 +323,13 @@ def _packed_weight(w: torch.Tensor, transposed: bool, nsplit: int) -> torch.Tens
     if hit is None:
         n, k = w.shape
         wd = w.detach()
-        hit = pack_split(wd, k, n, 1, k, nsplit) if transposed else pack_split(wd, n, k, k, 1, nsplit)
+        planes = pack_split(wd, k, n, 1, k, nsplit) if transposed else pack_split(wd, n, k, k, 1, nsplit)
         if len(_WEIGHT_CACHE) > 512:
             _WEIGHT_CACHE.clear()
-        _WEIGHT_CACHE[key] = hit
-    return hit
+        # the entry keeps the weight's storage alive: a freed weight's address could otherwise be handed to a
+        # new parameter of the same shape and hit this entry with stale planes
+        hit = _WEIGHT_CACHE[key] = (planes, wd)
+    return hit[0]
 
 
 class _Linear(torch.autograd.Function):

@@ -130,6 +130,30 @@ class SharedMLP(nn.Sequential):
                     h = mod(h)
         return h.view(b, p, s, -1).permute(0, 3, 1, 2)
 
+    def forward_max_pooled(self, x):
+        """relu(bn(conv(.))) blocks followed by the max over the last (nsample) axis, as one fused autograd
+        node (sa_mlp.shared_mlp_max): (B, C, npoint, nsample) -> (B, C_out, npoint).  Returns None when the
+        fused path does not apply (CPU, eval mode, other block layouts); the caller then runs forward() and
+        pools itself."""
+        from .. import sa_mlp
+
+        if x.dim() != 4 or not x.is_cuda or not torch.is_grad_enabled():
+            return None
+        blocks = []
+        for block in self:
+            mods = list(block.children())
+            if (len(mods) != 3 or not isinstance(mods[0], nn.Conv2d) or mods[0].kernel_size != (1, 1)
+                    or not isinstance(mods[1], _NormWrap) or not isinstance(mods[1][0], nn.BatchNorm2d)
+                    or not isinstance(mods[2], nn.ReLU)):
+                return None
+            blocks.append((mods[0], mods[1][0]))
+        b, c, p, s = x.shape
+        rows = x.permute(0, 2, 3, 1).reshape(b * p * s, c)
+        if not sa_mlp.applicable(rows, blocks, s):
+            return None
+        pooled = sa_mlp.shared_mlp_max(rows, blocks, s)          # (B * npoint, C_out)
+        return pooled.view(b, p, -1).permute(0, 2, 1)
+
     def __init__(self, args: List[int], *, bn: bool = False, activation=nn.ReLU(inplace=True),
                  preact: bool = False, first: bool = False, name: str = ""):
         super().__init__()

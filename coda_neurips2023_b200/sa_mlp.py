@@ -1,0 +1,196 @@
+"""The PointNet++ shared MLP + max over neighbours as ONE autograd node (training mode, CUDA).
+
+Mirror of `SharedMLP` (third_party_pointnet2/pointnet2/pytorch_utils.py:8-33: Conv2d 1x1 -> BatchNorm2d ->
+ReLU blocks) followed by the `F.max_pool2d(kernel_size=[1, nsample])` of `PointnetSAModuleVotes.forward`
+(pointnet2_modules.py:247-254), on channels-last rows (B * npoint * nsample, C):
+
+    layer 0      rows_linear_small_k (C_in = 3: exact fp32 FMAs)            -> y0
+    layer l > 0  tcgen05 split-bf16 GEMM on the planes written by layer l-1 -> y_l
+    between      BatchNorm statistics (one read of y_l), then normalise + ReLU + split into bf16 operand
+                 planes in one pass (the fp32 activation is never written); the last layer instead folds
+                 the max over the `nsample` rows of each seed in and returns (B * npoint, C) + arg-max
+    backward     per layer: masked BatchNorm-backward sums (one read of y_l and the incoming gradient), then
+                 dy written directly as the operand planes of the two gradient GEMMs (dW = dy^T a_{l-1} on
+                 MN-major operands, dz_{l-1} = dy W_l); layer 0 accumulates its (C_out x 3) dW in that pass.
+
+Kernels: csrc/sa_mlp_kernels.cu (include/coda_sa_mlp.h).  There is no CPU / eager fallback in here: callers
+(`SharedMLP.forward_max_pooled`) check `applicable()` first and use the module-by-module path otherwise.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import check, lib, ptr, stream_of
+
+_i, _ll, _f = ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+BACKWARD_PLANES = 2
+
+
+def _channels_ok(c: int) -> bool:
+    return 4 <= c <= 1024 and c % 4 == 0 and 256 % (c // 4) == 0
+
+
+def applicable(x: torch.Tensor, blocks, group: int) -> bool:
+    """blocks: list of (conv, bn) module pairs in execution order (each followed by ReLU)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and 1 <= group <= 256) or len(blocks) == 0:
+        return False
+    cin = x.shape[-1]
+    if cin > 8 and cin % 64 != 0:
+        return False
+    if cin <= 8 and x.requires_grad and torch.is_grad_enabled():
+        return False                      # the tiny-K first layer does not produce an input gradient
+    for li, (conv, bn) in enumerate(blocks):
+        cout = conv.weight.shape[0]
+        if conv.bias is not None or not bn.training or not bn.affine or not _channels_ok(cout):
+            return False
+        if li < len(blocks) - 1 and cout % 64 != 0:
+            return False
+    return True
+
+
+def _scratch(c: int, device) -> torch.Tensor:
+    lib().coda_bn_rows_scratch_floats.restype = ctypes.c_longlong
+    return torch.empty(int(lib().coda_bn_rows_scratch_floats(_i(c))), dtype=torch.float32, device=device)
+
+
+def _stats(y: torch.Tensor, bn: nn.modules.batchnorm._BatchNorm):
+    rows, c = y.shape
+    momentum = 0.0 if bn.momentum is None else float(bn.momentum)
+    track = bn.track_running_stats and bn.running_mean is not None
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            raise NotImplementedError("cumulative-average BatchNorm momentum is not on the CoDA path")
+    mean = torch.empty(c, dtype=torch.float32, device=y.device)
+    invstd = torch.empty(c, dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        st = lib().coda_bn_rows_stats(_ll(rows), _i(c), ptr(y), _f(bn.eps), _f(momentum),
+                                      ptr(bn.running_mean if track else None), ptr(bn.running_var if track else None),
+                                      ptr(mean), ptr(invstd), ptr(_scratch(c, y.device)), stream_of(y))
+    check(st, "bn_rows_stats")
+    return mean, invstd
+
+
+class _SharedMLPMax(torch.autograd.Function):
+    """forward(x_rows (R, C0), group, nsplit, bns, W0, g0, b0, W1, g1, b1, ...) -> pooled (R / group, C_last)"""
+
+    @staticmethod
+    def forward(ctx, x, group, nsplit, bns, *params):
+        L = lib()
+        nl = len(bns)
+        rows, c0 = x.shape
+        dev = x.device
+        ys, means, invstds, acts = [], [], [], []
+        small_k = c0 <= 8
+        cur = None
+        with torch.cuda.device(dev):
+            for li in range(nl):
+                w, gamma, beta = params[3 * li: 3 * li + 3]
+                cout, cin = w.shape
+                if li == 0 and small_k:
+                    y = torch.empty((rows, cout), dtype=torch.float32, device=dev)
+                    check(L.coda_rows_linear_small_k(_ll(rows), _i(cin), _i(cout), ptr(x), ptr(w.contiguous()), ptr(y),
+                                                     stream_of(x)), "rows_linear_small_k")
+                else:
+                    if li == 0:
+                        cur = ops.pack_split(x, rows, c0, c0, 1, nsplit)
+                    y = ops.gemm_nt(cur, ops._packed_weight(w, False, nsplit), rows, cout)[0]
+                mean, invstd = _stats(y, bns[li])
+                ys.append(y); means.append(mean); invstds.append(invstd)
+                if li < nl - 1:
+                    nxt = torch.empty((nsplit, 1, rows, cout), dtype=torch.bfloat16, device=dev)
+                    check(L.coda_bn_relu_pack_rows(_ll(rows), _i(cout), _i(nsplit), ptr(y), ptr(mean), ptr(invstd),
+                                                   ptr(gamma), ptr(beta), ptr(nxt), stream_of(x)), "bn_relu_pack_rows")
+                    acts.append(cur)      # operand planes of THIS layer's input (None for the tiny-K layer)
+                    cur = nxt
+                else:
+                    acts.append(cur)
+                    groups = rows // group
+                    pooled = torch.empty((groups, cout), dtype=torch.float32, device=dev)
+                    argmax = torch.empty((groups, cout), dtype=torch.uint8, device=dev)
+                    check(L.coda_bn_relu_maxpool_rows(_ll(groups), _i(group), _i(cout), ptr(y), ptr(mean), ptr(invstd),
+                                                      ptr(gamma), ptr(beta), ptr(pooled), ptr(argmax), stream_of(x)),
+                          "bn_relu_maxpool_rows")
+        ctx.nl, ctx.group, ctx.small_k = nl, group, small_k
+        ctx.acts = acts                       # bf16 planes: not autograd inputs, kept by reference
+        ctx.save_for_backward(x, argmax, *ys, *means, *invstds, *params)
+        ctx.mark_non_differentiable(argmax)
+        return pooled, argmax
+
+    @staticmethod
+    def backward(ctx, dpooled, _dargmax):
+        L = lib()
+        nl, group = ctx.nl, ctx.group
+        saved = ctx.saved_tensors
+        x, argmax = saved[0], saved[1]
+        ys = saved[2: 2 + nl]
+        means = saved[2 + nl: 2 + 2 * nl]
+        invstds = saved[2 + 2 * nl: 2 + 3 * nl]
+        params = saved[2 + 3 * nl:]
+        rows = x.shape[0]
+        dev = x.device
+        ns = BACKWARD_PLANES
+        grads = [None] * (3 * nl)
+        dx = None
+        dz = None
+        dpooled = dpooled.contiguous()
+        with torch.cuda.device(dev):
+            for li in range(nl - 1, -1, -1):
+                w, gamma, beta = params[3 * li: 3 * li + 3]
+                cout, cin = w.shape
+                y, mean, invstd = ys[li], means[li], invstds[li]
+                s1 = torch.empty(cout, dtype=torch.float32, device=dev)
+                s2 = torch.empty(cout, dtype=torch.float32, device=dev)
+                scratch = _scratch(cout, dev)
+                if li == nl - 1:
+                    check(L.coda_bn_relu_bwd_reduce_pooled(_ll(rows // group), _i(group), _i(cout), ptr(y), ptr(dpooled),
+                                                           ptr(argmax), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta),
+                                                           ptr(s1), ptr(s2), ptr(scratch), stream_of(x)),
+                          "bn_relu_bwd_reduce_pooled")
+                else:
+                    check(L.coda_bn_relu_bwd_reduce(_ll(rows), _i(cout), ptr(y), ptr(dz), ptr(mean), ptr(invstd),
+                                                    ptr(gamma), ptr(beta), ptr(s1), ptr(s2), ptr(scratch), stream_of(x)),
+                          "bn_relu_bwd_reduce")
+                grads[3 * li + 1], grads[3 * li + 2] = s2, s1            # dgamma, dbeta
+                if li == 0 and ctx.small_k:
+                    if nl == 1:   # single block: expand the pooled gradient (not a CoDA configuration)
+                        dz = torch.zeros((rows // group, group, cout), dtype=torch.float32, device=dev)
+                        dz.scatter_(1, argmax.long().unsqueeze(1), dpooled.unsqueeze(1))
+                        dz = dz.view(rows, cout)
+                    L.coda_bn_rows_small_k_scratch_floats.restype = ctypes.c_longlong
+                    sc = torch.empty(int(L.coda_bn_rows_small_k_scratch_floats(_i(cin), _i(cout))), dtype=torch.float32,
+                                     device=dev)
+                    dw = torch.empty((cout, cin), dtype=torch.float32, device=dev)
+                    check(L.coda_bn_relu_bwd_small_k(_ll(rows), _i(cin), _i(cout), ptr(y), ptr(dz), ptr(mean), ptr(invstd),
+                                                     ptr(gamma), ptr(beta), ptr(s1), ptr(s2), ptr(x), ptr(dw), ptr(sc),
+                                                     stream_of(x)), "bn_relu_bwd_small_k")
+                    grads[0] = dw
+                    break
+                dy = torch.empty((ns, 1, rows, cout), dtype=torch.bfloat16, device=dev)
+                pooled_form = li == nl - 1
+                check(L.coda_bn_relu_bwd_pack(_ll(rows), _i(cout), _i(ns), ptr(y), ptr(None if pooled_form else dz),
+                                              ptr(dpooled if pooled_form else None), ptr(argmax if pooled_form else None),
+                                              _i(group), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(s1), ptr(s2),
+                                              ptr(dy), stream_of(x)), "bn_relu_bwd_pack")
+                a_prev = ctx.acts[li]
+                grads[3 * li] = ops.gemm_tn(dy, a_prev[:ns], cout, cin)              # dW = dy^T a_{l-1}
+                if li > 0 or ctx.needs_input_grad[0]:
+                    dz = ops.gemm_nt(dy, ops._packed_weight(w, True, ns), rows, cin)[0]  # gradient of the layer input
+                    if li == 0:
+                        dx = dz
+        return (dx, None, None, None, *grads)
+
+
+def shared_mlp_max(x_rows: torch.Tensor, blocks, group: int, nsplit: int | None = None) -> torch.Tensor:
+    """x_rows (R, C0) channels-last grouped features -> (R / group, C_last): max over each run of `group` rows of
+    relu(bn(conv(...))).  `blocks` = [(conv, bn), ...] (1x1 Conv2d without bias, BatchNorm2d in training mode)."""
+    params = []
+    for conv, bn in blocks:
+        params += [conv.weight.reshape(conv.weight.shape[0], -1), bn.weight, bn.bias]
+    pooled, _ = _SharedMLPMax.apply(x_rows.contiguous(), int(group), ops.DEFAULT_NSPLIT if nsplit is None else nsplit,
+                                    [bn for _, bn in blocks], *params)
+    return pooled
