@@ -74,7 +74,9 @@ constexpr int BK = 64;  // 64 x 2 B = one 128-byte swizzle span
 struct GemmMaps {
   CUtensorMap a[3];
   CUtensorMap b[3];
+  CUtensorMap c;   // output, for the TMA-store epilogue (valid when the kernel's tma_store flag is set)
 };
+constexpr int EPI_STAGE = 4 * 32 * 128;   // four epilogue warps x [32 rows x 128 B] staging tiles
 
 // which (A plane, B plane) pairs are multiplied; small cross terms first
 __host__ __device__ constexpr int n_products(int ns) { return ns == 1 ? 1 : (ns == 2 ? 3 : 6); }
@@ -93,7 +95,7 @@ template <int NSPLIT, int BN, int STAGES, bool FP16, bool MN>
 __global__ void __launch_bounds__(256, 1)
 gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, int b_batched, int ksplit, int batch_n,
                const float *__restrict__ bias_in, int act, int out_half, void *__restrict__ c_void, long long ldc,
-               long long c_batch_stride) {
+               long long c_batch_stride, int tma_store) {
   // PERSISTENT: each CTA walks work items w = blockIdx.x, blockIdx.x + gridDim.x, ...;  a work item is
   // (m-tile, n-tile, batch, k-split).  The accumulator is double-buffered in TMEM (2 x BN columns) so
   // the epilogue warps drain tile i while the MMA warp already accumulates tile i+1.
@@ -228,6 +230,83 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + buf * ACC_COLS;
       float *crow = c + (size_t)batch * c_batch_stride + (size_t)row * ldc;
+      if (tma_store) {
+        // coalesced epilogue: the warp's [32 rows x 128 B] chunk goes through a 128B-swizzled staging tile and
+        // leaves as ONE bulk tensor store (full lines, clipped at the matrix edge, asynchronous)
+        unsigned char *stage = smem + (size_t)STAGES * STAGE + (size_t)q * (32 * 128);
+        unsigned char *srow = stage + lane * 128;
+        const int sw = lane & 7;
+        constexpr int CHUNK = FP16 ? 64 : 32;   // output columns per staging tile (fp16 out only with fp16 operands)
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += CHUNK) {
+          const int col0 = n0 + c0;
+          if (col0 >= n) break;                 // warp-uniform
+          float v[CHUNK];
+          {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) v[t] = __uint_as_float(r[t]);
+            if (CHUNK == 64) {
+              tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 32), r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int t = 0; t < 32; ++t) v[(CHUNK == 64 ? 32 : 0) + t] = __uint_as_float(r[t]);
+            }
+          }
+          if (bias) {
+            if (col0 + CHUNK <= n) {
+#pragma unroll
+              for (int t = 0; t < CHUNK; t += 4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col0 + t));
+                v[t] += bb.x; v[t + 1] += bb.y; v[t + 2] += bb.z; v[t + 3] += bb.w;
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < CHUNK; ++t)
+                if (col0 + t < n) v[t] += __ldg(bias + col0 + t);
+            }
+          }
+          if (act == 1) {
+#pragma unroll
+            for (int t = 0; t < CHUNK; ++t) v[t] = fmaxf(v[t], 0.f);
+          } else if (act == 2) {
+#pragma unroll
+            for (int t = 0; t < CHUNK; ++t) v[t] = __fdividef(v[t], 1.0f + __expf(-1.702f * v[t]));
+          }
+          // the previous chunk's store must have read the staging tile before it is rewritten
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {   // eight 16-byte pieces per 128-byte row, XOR-swizzled by the row
+            uint4 pk;
+            if (FP16) {
+              const __half2 h0 = __floats2half2_rn(v[(FP16 ? 8 : 0) * j + 0], v[(FP16 ? 8 : 0) * j + 1]);
+              const __half2 h1 = __floats2half2_rn(v[(FP16 ? 8 : 0) * j + 2], v[(FP16 ? 8 : 0) * j + 3]);
+              const __half2 h2 = __floats2half2_rn(v[(FP16 ? 8 : 0) * j + 4], v[(FP16 ? 8 : 0) * j + 5]);
+              const __half2 h3 = __floats2half2_rn(v[(FP16 ? 8 : 0) * j + 6], v[(FP16 ? 8 : 0) * j + 7]);
+              pk.x = *reinterpret_cast<const uint32_t *>(&h0); pk.y = *reinterpret_cast<const uint32_t *>(&h1);
+              pk.z = *reinterpret_cast<const uint32_t *>(&h2); pk.w = *reinterpret_cast<const uint32_t *>(&h3);
+            } else {
+              pk = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                              __float_as_uint(v[4 * j + 3]));
+            }
+            *reinterpret_cast<uint4 *>(srow + ((j ^ sw) << 4)) = pk;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&maps.c, stage, col0, m0 + q * 32, batch);
+            tma_store_commit();
+          }
+        }
+        if (lane == 0) tma_store_wait_read();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        continue;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
@@ -344,8 +423,20 @@ int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_b
       ez = cudaMemset2DAsync(c + (size_t)bi * c_batch_stride, (size_t)ldc * 4, 0, (size_t)n * 4, (size_t)m, s);
     if (ez != cudaSuccess) return (int)ez;
   }
-  constexpr size_t smem = (size_t)STAGES * NSPLIT * (BM * BK * 2 + BN * BK * 2) + 1024;
+  constexpr size_t smem = (size_t)STAGES * NSPLIT * (BM * BK * 2 + BN * BK * 2) + EPI_STAGE + 1024;
   auto kern = gemm_nt_kernel<NSPLIT, BN, STAGES, FP16, MN>;
+  // TMA-store epilogue whenever the output satisfies the tensor-map rules (16-byte aligned rows); fp16 output
+  // exists only on the fp16-operand instances
+  GemmMaps lmaps = maps;
+  int tma_store = 0;
+  if (ksplit == 1 && (!out_half || FP16) && (out_half != 0) == FP16) {
+    const long long align = out_half ? 8 : 4;
+    if (ldc % align == 0 && c_batch_stride % align == 0 && ((uintptr_t)c_out & 15) == 0) {
+      const int st = out_half ? make_tmap_k_major_16b(&lmaps.c, c_out, 1, n, m, batch, ldc, c_batch_stride, 32)
+                              : make_tmap_rows_f32(&lmaps.c, c_out, n, m, batch, ldc, c_batch_stride);
+      tma_store = st == CODA_OK;
+    }
+  }
   static bool configured = false;  // once per template instance
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -361,8 +452,8 @@ int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_b
     if (num_sms <= 0) num_sms = 148;
   }
   const unsigned grid = (unsigned)(nwork < num_sms ? nwork : num_sms);
-  kern<<<grid, 256, smem, s>>>(maps, m, n, kpad, b_batched, ksplit, batch, bias, relu, out_half, c_out, ldc,
-                               c_batch_stride);
+  kern<<<grid, 256, smem, s>>>(lmaps, m, n, kpad, b_batched, ksplit, batch, bias, relu, out_half, c_out, ldc,
+                               c_batch_stride, tma_store);
   return launch_status();
 }
 
@@ -445,7 +536,7 @@ int coda_gemm_nt_ex(int nsplit, int is_fp16, int batch, int m, int n, int kpad, 
     if (bn == 64) CODA_GEMM(2, 64, 4, false);
     CODA_GEMM(2, 128, 3, false);
   }
-  if (bn == 64) CODA_GEMM(3, 64, 3, false);
+  if (bn == 64) CODA_GEMM(3, 64, 2, false);
   CODA_GEMM(3, 128, 2, false);
 #undef CODA_GEMM
 }
@@ -473,7 +564,7 @@ int coda_gemm_tn(int nsplit, int mc, int m, int n, const void *a, long long a_pl
   return launch_gemm<NS, BN_, ST, false, true>(maps, 1, m, n, kpad, 0, nullptr, 0, c, ldc, 0, s)
   if (nsplit == 1) { if (bn == 64) CODA_GEMM_TN(1, 64, 6); CODA_GEMM_TN(1, 128, 6); }
   if (nsplit == 2) { if (bn == 64) CODA_GEMM_TN(2, 64, 4); CODA_GEMM_TN(2, 128, 3); }
-  if (bn == 64) CODA_GEMM_TN(3, 64, 3);
+  if (bn == 64) CODA_GEMM_TN(3, 64, 2);
   CODA_GEMM_TN(3, 128, 2);
 #undef CODA_GEMM_TN
 }

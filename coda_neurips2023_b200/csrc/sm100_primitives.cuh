@@ -43,6 +43,21 @@ inline int make_tmap_k_major_16b(CUtensorMap *map, const void *base, int is_fp16
   return r == CUDA_SUCCESS ? CODA_OK : CODA_EINVAL;
 }
 
+// fp32 output tiles for TMA stores: tensor [batch][rows][cols], box = [1][32][32] (32 x 4 B = one swizzle span)
+inline int make_tmap_rows_f32(CUtensorMap *map, const void *base, long long cols, long long rows, long long batch,
+                              long long row_stride, long long batch_stride) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return CODA_EINVAL;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t gstride[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)(batch > 1 ? batch_stride : row_stride * rows) * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CODA_OK : CODA_EINVAL;
+}
+
 // --------------------------------------------------------------------- device: TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -55,6 +70,17 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+
+// shared -> global tile store (bulk async group of the issuing thread); out-of-range rows / columns are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the shared-memory source of every committed store of this thread has been read (it may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // --------------------------------------------------------------------- device: tcgen05
 // One lane of a converged warp.  The MMA-issuing warp runs its control flow warp-uniformly and predicates
