@@ -29,20 +29,6 @@ namespace {
 constexpr int NS = 2;           // planes per operand in the backward
 constexpr int NPROD = 3;
 
-// rows pack: src (L, B, H*hd) -> planes [NS][B*H][L][hd]
-__global__ void __launch_bounds__(256)
-bwd_pack_rows_kernel(int L, int B, int H, int hd, float scale, const float *__restrict__ src,
-                     __nv_bfloat16 *__restrict__ planes) {
-  const long long total = (long long)L * B * H * hd;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int d = (int)(i % hd);
-  long long t = i / hd;
-  const int h = (int)(t % H); t /= H;
-  const int b = (int)(t % B);
-  const int l = (int)(t / B);
-  split3<NS>(__ldg(src + i) * scale, planes + (((size_t)(b * H + h)) * L + l) * hd + d, (size_t)total);
-}
 // D[bh][q] = sum_d dO * O   (both (Lq, B, H*hd)); one warp per (q, b, h)
 __global__ void __launch_bounds__(256)
 bwd_delta_kernel(int Lq, int B, int H, int hd, const float *__restrict__ dout, const float *__restrict__ out,
@@ -553,11 +539,14 @@ int coda_attention_bwd(int b, int h, int lq, int lk, int hd, float scale, const 
   __nv_bfloat16 *kp = w;                                   w += (size_t)NS * bh * lk * hd;
   __nv_bfloat16 *vp = w;                                   w += (size_t)NS * bh * lk * hd;
   float *delta = (float *)(((uintptr_t)w + 255) & ~(uintptr_t)255);
-  const long long tq = (long long)lq * bh * hd, tk = (long long)lk * bh * hd;
-  bwd_pack_rows_kernel<<<(unsigned)((tq + 255) / 256), 256, 0, s>>>(lq, b, h, hd, scale, q, qp);
-  bwd_pack_rows_kernel<<<(unsigned)((tq + 255) / 256), 256, 0, s>>>(lq, b, h, hd, 1.0f, dout, dop);
-  bwd_pack_rows_kernel<<<(unsigned)((tk + 255) / 256), 256, 0, s>>>(lk, b, h, hd, 1.0f, k, kp);
-  bwd_pack_rows_kernel<<<(unsigned)((tk + 255) / 256), 256, 0, s>>>(lk, b, h, hd, 1.0f, v, vp);
+  if ((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)dout) & 15) != 0) return CODA_EINVAL;
+  PackJobs jobs = {};
+  jobs.job[0] = {q, qp, lq, scale};
+  jobs.job[1] = {dout, dop, lq, 1.0f};
+  jobs.job[2] = {k, kp, lk, 1.0f};
+  jobs.job[3] = {v, vp, lk, 1.0f};
+  const long long t4 = (long long)(lq > lk ? lq : lk) * bh * hd / 4;
+  pack_rows_multi_kernel<NS><<<dim3((unsigned)((t4 + 255) / 256), 4), 256, 0, s>>>(jobs, b, h, hd);
   bwd_delta_kernel<<<(unsigned)(((long long)lq * bh * 32 + 255) / 256), 256, 0, s>>>(lq, b, h, hd, dout, out, delta);
   int st = launch_status();
   if (st != CODA_OK) return st;

@@ -36,6 +36,48 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16 *dst, size_t plane
   }
 }
 
+// Several (L, B, H*hd) fp32 tensors -> row planes [NS][B*H][L][hd] in ONE launch: blockIdx.y selects the
+// tensor, a thread converts four consecutive head-dim elements (16-byte load, 8-byte store per plane).
+struct PackJob {
+  const float *src;
+  __nv_bfloat16 *planes;
+  int L;
+  float scale;
+};
+struct PackJobs {
+  PackJob job[4];
+};
+template <int NSPLIT>
+__global__ void __launch_bounds__(256)
+pack_rows_multi_kernel(const __grid_constant__ PackJobs jobs, int B, int H, int hd) {
+  const PackJob jb = jobs.job[blockIdx.y];
+  const long long total4 = (long long)jb.L * B * H * hd / 4;
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const int hd4 = hd >> 2;
+  const int d = (int)(i4 % hd4) * 4;
+  long long t = i4 / hd4;
+  const int h = (int)(t % H); t /= H;
+  const int b = (int)(t % B);
+  const int l = (int)(t / B);
+  const float4 v = __ldg(reinterpret_cast<const float4 *>(jb.src) + i4);
+  float r[4] = {v.x * jb.scale, v.y * jb.scale, v.z * jb.scale, v.w * jb.scale};
+  __nv_bfloat16 *dst = jb.planes + (((size_t)(b * H + h)) * jb.L + l) * hd + d;
+  const size_t plane_stride = (size_t)total4 * 4;
+#pragma unroll
+  for (int p = 0; p < NSPLIT; ++p) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
+    uint2 w;
+    w.x = *reinterpret_cast<const uint32_t *>(&lo);
+    w.y = *reinterpret_cast<const uint32_t *>(&hi);
+    *reinterpret_cast<uint2 *>(dst + (size_t)p * plane_stride) = w;
+    if (p + 1 < NSPLIT) {
+      r[0] -= __uint_as_float(w.x << 16); r[1] -= __uint_as_float(w.x & 0xFFFF0000u);
+      r[2] -= __uint_as_float(w.y << 16); r[3] -= __uint_as_float(w.y & 0xFFFF0000u);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ dropout mask (counter hash)
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
   h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;

@@ -11,8 +11,8 @@
 // ex2 per element; the log-sum-exp is returned in natural-log units.
 //
 // One CTA = one (batch*head, 128-query tile); loop over 64-key tiles:
-//   warp 0 lane 0 : TMA producer of Q (once) and K_j;  warp 3 lane 0 : TMA producer of V^T_j
-//                   (K / V double-buffered for head dim 64)
+//   warp 0 lane 0 : TMA producer of K_j;  warp 3 lane 0 : TMA producer of V_j (row-major tiles, consumed as
+//                   MN-major B operands: no transposed copy of V exists);  4 / 2 stages for head dim 64 / 128
 //   warp 1 lane 0 : MMA issuer   S_j = Q K_j^T -> TMEM[64 (j&1), +64) (double-buffered: S_{j+1} is
 //                   queued before O_j);  O_j = P_j V_j -> TMEM[128 + HD (j % NWG), +HD)
 //   warp 2        : TMEM alloc / dealloc
@@ -29,43 +29,6 @@ using namespace coda;
 using namespace coda::attn;
 
 namespace {
-
-template <int NSPLIT>
-__global__ void __launch_bounds__(256)
-attn_pack_rows_kernel(int L, int B, int H, int HD, float scale, const float *__restrict__ src,
-                      __nv_bfloat16 *__restrict__ planes) {
-  const long long total = (long long)L * B * H * HD;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  // i enumerates src order: ((l * B + b) * H + h) * HD + d
-  const int d = (int)(i % HD);
-  long long t = i / HD;
-  const int h = (int)(t % H); t /= H;
-  const int b = (int)(t % B);
-  const int l = (int)(t / B);
-  const size_t o = (((size_t)(b * H + h)) * L + l) * HD + d;
-  split3<NSPLIT>(__ldg(src + i) * scale, planes + o, (size_t)total);
-}
-
-template <int NSPLIT>
-__global__ void __launch_bounds__(256)
-attn_pack_vt_kernel(int L, int Lpad, int B, int H, int HD, const float *__restrict__ src,
-                    __nv_bfloat16 *__restrict__ planes) {
-  __shared__ float tile[32][33];
-  const int bh = blockIdx.z, b = bh / H, h = bh % H;
-  const int l0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int i = ty; i < 32; i += 8) {
-    const int l = l0 + i, d = d0 + tx;
-    tile[i][tx] = (l < L && d < HD) ? __ldg(src + ((size_t)l * B + b) * H * HD + (size_t)h * HD + d) : 0.f;
-  }
-  __syncthreads();
-  const size_t plane = (size_t)B * H * HD * Lpad;
-  for (int i = ty; i < 32; i += 8) {
-    const int d = d0 + i, l = l0 + tx;
-    if (d < HD && l < Lpad) split3<NSPLIT>(tile[tx][i], planes + ((size_t)bh * HD + d) * Lpad + l, plane);
-  }
-}
 
 // materialised keep-mask * 1/(1-p) for the interim (cuBLAS) backward: mult[bh][q][k] in {0, 1/(1-p)}
 __global__ void __launch_bounds__(256)
@@ -111,7 +74,7 @@ struct AttnCfg {
   static constexpr int NP = p_planes(NSPLIT);
   static constexpr int KB = HD / 64;                       // 64-wide k-blocks of the head dim
   static constexpr int K_PLANE = KT * HD * 2;              // KB blocks of [64 x 64]
-  static constexpr int V_PLANE = HD * KT * 2;              // [HD x 64]
+  static constexpr int V_PLANE = KT * HD * 2;              // KB blocks of [64 keys x 64]: V_j row-major, used MN-major
   static constexpr int K_STAGE = NSPLIT * K_PLANE;
   static constexpr int V_STAGE = NSPLIT * V_PLANE;
   static constexpr int K_OFF = 0;
@@ -197,14 +160,17 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
     }
   } else if (warp == 3) {
     if (lane == 0) {
-      // ===== TMA producer of V^T_j (own thread: a K load never queues behind a V stage still in use) =====
+      // ===== TMA producer of V_j (own thread: a K load never queues behind a V stage still in use) =====
       for (int j = 0; j < ntiles; ++j) {
         const int st = j % NST;
         mbar_wait(&v_empty[st], ((uint32_t)(j / NST) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&v_full[st], (uint32_t)SM::V_STAGE);
 #pragma unroll
         for (int p = 0; p < NSPLIT; ++p)
-          tma_load_3d(smem + SM::V_OFF + st * SM::V_STAGE + p * SM::V_PLANE, &maps.v[p], &v_full[st], j * KT, 0, bh);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_3d(smem + SM::V_OFF + st * SM::V_STAGE + p * SM::V_PLANE + kb * (KT * 128), &maps.v[p],
+                        &v_full[st], kb * 64, j * KT, bh);
       }
     }
   } else if (warp == 1) {
@@ -212,7 +178,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
     //       tiles ahead of O_j = P_j V_j so the tensor pipe works on the next scores while the softmax
     //       warps are busy with the current ones =====
     constexpr uint32_t idesc_s = umma_idesc_f16(0, QT, KT);  // 128 x 64
-    constexpr uint32_t idesc_o = umma_idesc_f16(0, QT, HD);  // 128 x HD
+    constexpr uint32_t idesc_o = umma_idesc_f16(0, QT, HD, 0, 1);  // 128 x HD; B = V_j, MN-major (hd contiguous)
     auto issue_s = [&](int j) {
       const int st = j % NST;
       mbar_wait(&k_full[st], (uint32_t)(j / NST) & 1u);
@@ -255,10 +221,10 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
 #pragma unroll
         for (int p = 0; p < pv_nprod(NSPLIT); ++p) {
           const uint32_t a = tmem_p + (uint32_t)(g * SM::P_COLS + pv_pa(NSPLIT, p) * (KT / 2));
-          const uint64_t bd = umma_smem_desc_k_sw128(smem + SM::V_OFF + st * SM::V_STAGE + pv_pb(NSPLIT, p) * SM::V_PLANE);
+          const uint64_t bd = umma_smem_desc_mn_sw128(smem + SM::V_OFF + st * SM::V_STAGE + pv_pb(NSPLIT, p) * SM::V_PLANE);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // 16 keys = 8 TMEM columns per MMA
-            umma_f16_ts(d, a + kk * 8, umma_desc_advance(bd, kk * 32), idesc_o, (uint32_t)((p | kk) != 0));
+          for (int kk = 0; kk < 4; ++kk)   // 16 keys = 8 TMEM columns of P, 16 rows x 128 B of V_j
+            umma_f16_ts(d, a + kk * 8, umma_desc_advance(bd, kk * 16 * 128), idesc_o, (uint32_t)((p | kk) != 0));
         }
         umma_commit(&v_empty[st]);
         umma_commit(&o_full[g]);
@@ -440,8 +406,7 @@ int launch_attn(const AttnMaps &maps, const __nv_bfloat16 *qplanes, int Lq, int 
 extern "C" {
 
 long long coda_attention_workspace_bytes(int b, int h, int lq, int lk, int hd, int nsplit) {
-  const long long lkpad = (lk + 63) / 64 * 64;
-  return 2LL * nsplit * b * h * ((long long)lq * hd + (long long)lk * hd + hd * lkpad) + 1024;
+  return 2LL * nsplit * b * h * ((long long)lq * hd + 2LL * lk * hd) + 1024;
 }
 
 static int attn_check(int b, int h, int lq, int lk, int hd, int nsplit) {
@@ -456,20 +421,22 @@ int coda_attention_pack(int b, int h, int lq, int lk, int hd, int nsplit, float 
   if (st != CODA_OK) return st;
   if (b == 0 || lq == 0) return CODA_OK;
   if (!q || !k || !v || !workspace) return CODA_EINVAL;
+  if ((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) != 0) return CODA_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   const int bh = b * h;
-  const int lkpad = (lk + 63) / 64 * 64;
   __nv_bfloat16 *qp = (__nv_bfloat16 *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   __nv_bfloat16 *kp = qp + (size_t)nsplit * bh * lq * hd;
   __nv_bfloat16 *vp = kp + (size_t)nsplit * bh * lk * hd;
-  const long long tq = (long long)lq * bh * hd, tk = (long long)lk * bh * hd;
-  const dim3 gvp((lkpad + 31) / 32, (hd + 31) / 32, bh);
-#define CODA_PACK(NS)                                                                                          \
-  attn_pack_rows_kernel<NS><<<(unsigned)((tq + 255) / 256), 256, 0, s>>>(lq, b, h, hd, scale * LOG2E, q, qp);           \
-  attn_pack_rows_kernel<NS><<<(unsigned)((tk + 255) / 256), 256, 0, s>>>(lk, b, h, hd, 1.0f, k, kp);            \
-  attn_pack_vt_kernel<NS><<<gvp, 256, 0, s>>>(lk, lkpad, b, h, hd, v, vp);
-  if (nsplit == 1) { CODA_PACK(1) } else if (nsplit == 2) { CODA_PACK(2) } else { CODA_PACK(3) }
-#undef CODA_PACK
+  // q carries scale * log2(e): the kernel's softmax works in base 2.  All three tensors in one launch.
+  PackJobs jobs = {};
+  jobs.job[0] = {q, qp, lq, scale * LOG2E};
+  jobs.job[1] = {k, kp, lk, 1.0f};
+  jobs.job[2] = {v, vp, lk, 1.0f};
+  const long long t4 = (long long)(lq > lk ? lq : lk) * bh * hd / 4;
+  const dim3 grid((unsigned)((t4 + 255) / 256), 3);
+  if (nsplit == 1) pack_rows_multi_kernel<1><<<grid, 256, 0, s>>>(jobs, b, h, hd);
+  else if (nsplit == 2) pack_rows_multi_kernel<2><<<grid, 256, 0, s>>>(jobs, b, h, hd);
+  else pack_rows_multi_kernel<3><<<grid, 256, 0, s>>>(jobs, b, h, hd);
   return launch_status();
 }
 
@@ -482,7 +449,6 @@ int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, 
   if (!out || !workspace || dropout_p < 0.f || dropout_p >= 1.f) return CODA_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   const int bh = b * h;
-  const int lkpad = (lk + 63) / 64 * 64;
   const __nv_bfloat16 *qp = (const __nv_bfloat16 *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   const __nv_bfloat16 *kp = qp + (size_t)nsplit * bh * lq * hd;
   const __nv_bfloat16 *vp = kp + (size_t)nsplit * bh * lk * hd;
@@ -490,8 +456,7 @@ int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, 
   for (int p = 0; p < nsplit; ++p) {
     st = make_tmap_k_major_16b(&maps.k[p], kp + (size_t)p * bh * lk * hd, 0, hd, lk, bh, hd, (long long)lk * hd, KT);
     if (st != CODA_OK) return st;
-    st = make_tmap_k_major_16b(&maps.v[p], vp + (size_t)p * bh * hd * lkpad, 0, lkpad, hd, bh, lkpad,
-                               (long long)hd * lkpad, hd);
+    st = make_tmap_k_major_16b(&maps.v[p], vp + (size_t)p * bh * lk * hd, 0, hd, lk, bh, hd, (long long)lk * hd, KT);
     if (st != CODA_OK) return st;
   }
 #define CODA_ATTN(HD_, NS) return launch_attn<HD_, NS>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s)
