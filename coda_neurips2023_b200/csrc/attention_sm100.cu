@@ -64,13 +64,16 @@ __host__ __device__ constexpr int pv_pb(int ns, int p) {  // plane of V
 // there once per CTA, the P planes by the softmax warps every tile.  Only K and V^T (the B operands) are
 // read from shared memory, which takes the 4 KB A-tile read per MMA off the shared-memory port -- with
 // eleven plane products per key tile that port, not the tensor pipe, was the limiter.
-template <int HD, int NSPLIT>
+// ONE_TILE: Lk <= 64 (the CLIP image tower: 50 tokens).  The whole problem is one key tile, so the CTA needs
+// a single K / V stage, half the tensor memory and no running accumulator: two CTAs share an SM and hide each
+// other's TMA / MMA / store latencies (one CTA per (crop, head) is otherwise all prologue).
+template <int HD, int NSPLIT, bool ONE_TILE = false>
 struct AttnCfg {
   // head dim 64: two softmax warpgroups take alternate key tiles (each with its own P / O buffers and its
   // own running max / sum, merged at the end).  head dim 128: one warpgroup (the O accumulator of a row
   // already fills its register budget).
-  static constexpr int NWG = HD == 64 ? 2 : 1;
-  static constexpr int NST = HD == 64 ? 4 : 2;             // K / V^T stages
+  static constexpr int NWG = (HD == 64 && !ONE_TILE) ? 2 : 1;
+  static constexpr int NST = ONE_TILE ? 1 : (HD == 64 ? 4 : 2);   // K / V stages
   static constexpr int NP = p_planes(NSPLIT);
   static constexpr int KB = HD / 64;                       // 64-wide k-blocks of the head dim
   static constexpr int K_PLANE = KT * HD * 2;              // KB blocks of [64 x 64]
@@ -83,12 +86,14 @@ struct AttnCfg {
   static constexpr int THREADS = 128 + NWG * 128;
   // TMEM columns (32-bit): S double buffer | O per warpgroup | P planes per warpgroup | Q planes
   static constexpr int S_COL = 0;
-  static constexpr int O_COL = 128;
+  static constexpr int O_COL = ONE_TILE ? 64 : 128;
+  static constexpr int TMEM_COLS = ONE_TILE ? 256 : 512;
+  static constexpr int MIN_CTAS = ONE_TILE ? 2 : 1;
   static constexpr int P_COL = O_COL + NWG * HD;
   static constexpr int P_COLS = NP * (KT / 2);             // bf16 pairs: 32 columns per plane
   static constexpr int Q_COL = P_COL + NWG * P_COLS;
   static constexpr int Q_COLS = HD / 2;                    // per plane
-  static_assert(Q_COL + NSPLIT * Q_COLS <= 512, "TMEM budget");
+  static_assert(Q_COL + NSPLIT * Q_COLS <= TMEM_COLS, "TMEM budget");
   static_assert(NWG == 1 || TOTAL >= QT * 64 * 4, "merge scratch must fit in the K/V stages");
 };
 
@@ -98,12 +103,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int HD, int NSPLIT>
-__global__ void __launch_bounds__(AttnCfg<HD, NSPLIT>::THREADS, 1)
+template <int HD, int NSPLIT, bool ONE_TILE>
+__global__ void __launch_bounds__(AttnCfg<HD, NSPLIT, ONE_TILE>::THREADS, AttnCfg<HD, NSPLIT, ONE_TILE>::MIN_CTAS)
 attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__restrict__ qplanes, int Lq, int Lk,
                 int B, int H, float *__restrict__ out, float *__restrict__ lse, float drop_p, uint32_t seed,
                 const uint32_t *__restrict__ seed_dev) {
-  using SM = AttnCfg<HD, NSPLIT>;
+  using SM = AttnCfg<HD, NSPLIT, ONE_TILE>;
   if (seed_dev) seed += __ldg(seed_dev);  // per-step counter kept on the device (CUDA-graph friendly)
   constexpr int KB = SM::KB, NWG = SM::NWG, NP = SM::NP, NST = SM::NST;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -116,7 +121,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * QT, bh = blockIdx.y;
   const int ntiles = (Lk + KT - 1) / KT;
-  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t TMEM_COLS = SM::TMEM_COLS;
 
   if (warp == 0 && lane == 0) {
 #pragma unroll
@@ -256,9 +261,9 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
       tc_fence_before();
       mbar_arrive(&q_full);
     }
-    float o_acc[HD];
+    float o_acc[ONE_TILE ? 1 : HD];   // running output (not needed when the single tile IS the output)
 #pragma unroll
-    for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
+    for (int d = 0; d < (ONE_TILE ? 1 : HD); ++d) o_acc[d] = 0.f;
     // scores arrive in log2 units (q was packed with scale * log2 e): p = 2^(s - m)
     float m_run = -INFINITY, l_run = 0.f;
     const bool dropout = drop_p > 0.f;
@@ -335,16 +340,38 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
       // O_j = P_j V_j, then o = o * alpha + O_j
       mbar_wait(&o_full[g], ph);
       tc_fence_after();
+      if constexpr (ONE_TILE) {
+        // the only tile: normalise and store straight from tensor memory
+        const int qrow = q0 + row;
+        const float inv = keep_scale / l_run;
+        const int b = bh / H, h = bh - b * H;
+        float *orow = out + ((size_t)qrow * B + b) * (size_t)(H * HD) + (size_t)h * HD;
 #pragma unroll
-      for (int c0 = 0; c0 < HD; c0 += 32) {
-        uint32_t orr[32];
-        tmem_ld_32x32(my_o + c0, orr);
-        tmem_ld_wait();
+        for (int c0 = 0; c0 < HD; c0 += 32) {
+          uint32_t orr[32];
+          tmem_ld_32x32(my_o + c0, orr);
+          tmem_ld_wait();
+          if (qrow < Lq) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t) o_acc[c0 + t] = o_acc[c0 + t] * alpha + __uint_as_float(orr[t]);
+            for (int t = 0; t < 32; t += 4)
+              *reinterpret_cast<float4 *>(orow + c0 + t) =
+                  make_float4(__uint_as_float(orr[t]) * inv, __uint_as_float(orr[t + 1]) * inv,
+                              __uint_as_float(orr[t + 2]) * inv, __uint_as_float(orr[t + 3]) * inv);
+          }
+        }
+        if (lse && qrow < Lq) lse[(size_t)bh * Lq + qrow] = m_run * LN2 + logf(l_run);
+      } else {
+#pragma unroll
+        for (int c0 = 0; c0 < HD; c0 += 32) {
+          uint32_t orr[32];
+          tmem_ld_32x32(my_o + c0, orr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) o_acc[c0 + t] = o_acc[c0 + t] * alpha + __uint_as_float(orr[t]);
+        }
       }
     }
-    if (NWG == 2) {
+    if constexpr (NWG == 2) {
       // ===== merge the two warpgroups' partial softmax states (disjoint key subsets) =====
       // every tile's o_full has been awaited by its owner, so after this barrier no MMA reads smem any more
       float *scratch = reinterpret_cast<float *>(smem);  // [HD][128] floats, row fastest
@@ -368,7 +395,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
     }
     // ===== epilogue: normalise, store (Lq, B, H*HD) and the log-sum-exp (natural-log units) =====
     const int qrow = q0 + row;
-    if (g == 0 && qrow < Lq) {
+    if (!ONE_TILE && g == 0 && qrow < Lq) {
       const float inv = keep_scale / l_run;
       const int b = bh / H, h = bh - b * H;
       float *orow = out + ((size_t)qrow * B + b) * (size_t)(H * HD) + (size_t)h * HD;
@@ -384,12 +411,12 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
   if (warp == 2) tmem_dealloc(tmem_slot, TMEM_COLS);
 }
 
-template <int HD, int NSPLIT>
+template <int HD, int NSPLIT, bool ONE_TILE = false>
 int launch_attn(const AttnMaps &maps, const __nv_bfloat16 *qplanes, int Lq, int Lk, int B, int H, float *out,
                 float *lse, float drop_p, uint32_t seed, const uint32_t *seed_dev, cudaStream_t s) {
-  using SM = AttnCfg<HD, NSPLIT>;
+  using SM = AttnCfg<HD, NSPLIT, ONE_TILE>;
   constexpr size_t smem = SM::TOTAL + 1024;
-  auto kern = attn_fwd_kernel<HD, NSPLIT>;
+  auto kern = attn_fwd_kernel<HD, NSPLIT, ONE_TILE>;
   static bool configured = false;  // once per template instance
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -460,6 +487,10 @@ int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, 
     if (st != CODA_OK) return st;
   }
 #define CODA_ATTN(HD_, NS) return launch_attn<HD_, NS>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s)
+  if (hd == 64 && lk <= KT && nsplit <= 2) {   // single key tile (CLIP image tower): two CTAs per SM
+    if (nsplit == 1) return launch_attn<64, 1, true>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s);
+    return launch_attn<64, 2, true>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s);
+  }
   if (hd == 64) {
     if (nsplit == 1) CODA_ATTN(64, 1);
     if (nsplit == 2) CODA_ATTN(64, 2);

@@ -45,6 +45,34 @@ pack_rows_kernel(long long rows, int k, int kpad, long long src_row_stride, cons
   split_store<NSPLIT>(x, planes + idx, (size_t)plane_stride);
 }
 
+// same, four consecutive k per thread (k % 4 == 0, 16-byte aligned rows): one 16-byte load, one 8-byte store per plane
+template <int NSPLIT>
+__global__ void __launch_bounds__(256)
+pack_rows_vec4_kernel(long long rows, int k, int kpad, long long src_row_stride, const float *__restrict__ src,
+                      float scale, __nv_bfloat16 *__restrict__ planes, long long plane_stride) {
+  const int kq = kpad >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * kq) return;
+  const long long r = idx / kq;
+  const int c = (int)(idx - r * kq) * 4;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < k) v = __ldg(reinterpret_cast<const float4 *>(src + r * src_row_stride + c));
+  float x[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+  __nv_bfloat16 *dst = planes + r * kpad + c;
+#pragma unroll
+  for (int p = 0; p < NSPLIT; ++p) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
+    uint2 w;
+    w.x = *reinterpret_cast<const uint32_t *>(&lo);
+    w.y = *reinterpret_cast<const uint32_t *>(&hi);
+    *reinterpret_cast<uint2 *>(dst + (size_t)p * plane_stride) = w;
+    if (p + 1 < NSPLIT) {
+      x[0] -= __uint_as_float(w.x << 16); x[1] -= __uint_as_float(w.x & 0xFFFF0000u);
+      x[2] -= __uint_as_float(w.y << 16); x[3] -= __uint_as_float(w.y & 0xFFFF0000u);
+    }
+  }
+}
+
 // source is contiguous along rows (src_row_stride == 1, "transposed" operand): 32x32 smem transpose
 template <int NSPLIT>
 __global__ void __launch_bounds__(256)
@@ -297,7 +325,8 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&maps.c, stage, col0, m0 + q * 32, batch);
+            if (tma_store == 2) tma_reduce_add_3d(&maps.c, stage, col0, m0 + q * 32, batch);   // split-K partial
+            else tma_store_3d(&maps.c, stage, col0, m0 + q * 32, batch);
             tma_store_commit();
           }
         }
@@ -429,12 +458,12 @@ int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_b
   // exists only on the fp16-operand instances
   GemmMaps lmaps = maps;
   int tma_store = 0;
-  if (ksplit == 1 && (!out_half || FP16) && (out_half != 0) == FP16) {
+  if ((ksplit == 1 || !out_half) && (!out_half || FP16) && (out_half != 0) == FP16) {
     const long long align = out_half ? 8 : 4;
     if (ldc % align == 0 && c_batch_stride % align == 0 && ((uintptr_t)c_out & 15) == 0) {
       const int st = out_half ? make_tmap_k_major_16b(&lmaps.c, c_out, 1, n, m, batch, ldc, c_batch_stride, 32)
                               : make_tmap_rows_f32(&lmaps.c, c_out, n, m, batch, ldc, c_batch_stride);
-      tma_store = st == CODA_OK;
+      tma_store = st == CODA_OK ? (ksplit > 1 ? 2 : 1) : 0;   // split-K: bulk reduce-add into the zeroed output
     }
   }
   static bool configured = false;  // once per template instance
@@ -469,7 +498,14 @@ int coda_pack_split_bf16_strided(long long rows, int k, int kpad, long long src_
   if (!src || !planes) return CODA_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   __nv_bfloat16 *out = (__nv_bfloat16 *)planes;
-  if (src_k_stride == 1 || k <= 1) {
+  if ((src_k_stride == 1 || k <= 1) && k % 4 == 0 && src_row_stride % 4 == 0 && ((uintptr_t)src & 15) == 0 &&
+      plane_stride % 4 == 0 && ((uintptr_t)out & 7) == 0) {
+    const long long total = rows * (kpad / 4);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (nsplit == 1) pack_rows_vec4_kernel<1><<<grid, 256, 0, s>>>(rows, k, kpad, src_row_stride, src, scale, out, plane_stride);
+    else if (nsplit == 2) pack_rows_vec4_kernel<2><<<grid, 256, 0, s>>>(rows, k, kpad, src_row_stride, src, scale, out, plane_stride);
+    else pack_rows_vec4_kernel<3><<<grid, 256, 0, s>>>(rows, k, kpad, src_row_stride, src, scale, out, plane_stride);
+  } else if (src_k_stride == 1 || k <= 1) {
     const long long total = rows * kpad;
     const unsigned grid = (unsigned)((total + 255) / 256);
     if (nsplit == 1) pack_rows_kernel<1><<<grid, 256, 0, s>>>(rows, k, kpad, src_row_stride, src, scale, out, plane_stride);
