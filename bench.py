@@ -218,6 +218,53 @@ def attention_roofline(a, device):
                     "algorithmic MMA; `achieved`/`frac` count algorithmic FLOPs only" % (ns, nprod)}
 
 
+def _time_launch(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def gemm_roofline(a, device):
+    """The dominant kernel by share of the step (profiles/r01_step_kernels_*.txt): the split-bf16 tcgen05 GEMM
+    instance gemm_nt_kernel<3,128,2> (every fp32 Linear / 1x1 conv forward), timed on its longest launch of the
+    step: the third set-abstraction layer, (B * 2048 seeds * 64 neighbours) rows x 128 -> 256 channels.  At this
+    shape the kernel streams: algorithmic bytes = the three bf16 planes of A read once + the fp32 output written
+    once (+ the 0.2 MB weight planes); peak = MEASURED_PEAKS.json hbm_gbs."""
+    from coda_neurips2023_b200 import ops
+
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    rows, k, n, ns = a.batch_per_gpu * 2048 * 64, 128, 256, a.nsplit
+    ap = torch.randn(ns, 1, rows, k, device=device).bfloat16()           # operand planes, as bn_relu_pack writes them
+    wp = ops.pack_split(torch.randn(n, k, device=device), n, k, k, 1, ns)
+    y = torch.empty(1, rows, n, device=device)
+    ms = _time_launch(lambda: ops.gemm_nt(ap, wp, rows, n, out=y))
+    nbytes = 2.0 * ns * rows * k + 4.0 * rows * n + 2.0 * ns * n * k
+    achieved = nbytes / (ms * 1e-3) / 1e9
+    flops = 2.0 * rows * n * k
+    return {"bound": "hbm", "kernel": "gemm_nt_kernel<%d,128,2> (tcgen05 split-bf16 GEMM; SA layer 3: %d x %d x %d, "
+            "fp32-class result from %d bf16 planes)" % (ns, rows, n, k, ns),
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+            "bytes_per_launch": nbytes, "ms_per_launch": ms,
+            "traffic": 1.89e9 if ns == 3 else None,
+            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this launch "
+                              "(profiles/r01_gemm_ncu.txt)" if ns == 3 else None,
+            "useful_tflops": flops / (ms * 1e-3) / 1e12,
+            "note": "working set (%.1f GB) >> 126 MB L2: every timed launch streams from HBM" % (nbytes / 1e9)}
+
+
 def run_ours(a):
     import torch.distributed as dist
 
@@ -334,7 +381,9 @@ def run_ours(a):
         "operand_split": a.nsplit, "param_spread_across_ranks": param_spread,
         "grad_allreduce_bytes": step.flat.nbytes(),
     }
-    line["roofline"] = attention_roofline(a, device)
+    line["roofline"] = gemm_roofline(a, device)
+    # the tensor-bound kernels next in line, same measurement method (kernel alone, CUDA events)
+    line["roofline_more"] = [attention_roofline(a, device)]
     if world == 1 and not a.no_cpu_baseline:
         threads = min(os.cpu_count() or 1, 32)  # more threads only slow these small CPU ops down
         rate, sec = cpu_step_rate(a, 1, 1, threads)

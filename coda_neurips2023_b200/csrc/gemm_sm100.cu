@@ -146,10 +146,20 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
   const int nkb_total = kpad / BK;
   const int per = (nkb_total + ksplit - 1) / ksplit;
 
-  // work item -> coordinates (m fastest: consecutive CTAs share the same B tile in L2)
+  // work item -> coordinates.  The CTAs that run concurrently should share operand tiles in L2: with few
+  // n-tiles (skinny weights, the step's shapes) n runs fastest, so the n-tiles of one m-tile are in flight
+  // together and the A rows are fetched from HBM once (ncu: the 1M x 256 x 128 SA layer read A twice when m
+  // ran fastest); with more n-tiles than m-tiles the roles swap.
+  const bool n_fast = tiles_n <= tiles_m;
   auto decode = [&](long long w, int &m0, int &n0, int &batch, int &ks) {
-    const int tm = (int)(w % tiles_m); w /= tiles_m;
-    const int tn = (int)(w % tiles_n); w /= tiles_n;
+    int tm, tn;
+    if (n_fast) {
+      tn = (int)(w % tiles_n); w /= tiles_n;
+      tm = (int)(w % tiles_m); w /= tiles_m;
+    } else {
+      tm = (int)(w % tiles_m); w /= tiles_m;
+      tn = (int)(w % tiles_n); w /= tiles_n;
+    }
     ks = (int)(w % ksplit);
     batch = (int)(w / ksplit);
     m0 = tm * BM; n0 = tn * BN;

@@ -14,10 +14,14 @@ which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("attn", "all"):
     q, k, v = (torch.randn(2048, 8, 256, device="cuda") for _ in range(3))
     for _ in range(3):
-        attention_launch.forward(q, k, v, 4)          # encoder self-attention, L = 2048, 4 x 64
+        out, lse = attention_launch.forward(q, k, v, 4, dropout_p=0.1, salt=5)   # encoder self-attention, L = 2048, 4 x 64
+    attention_launch.backward(q, k, v, out, torch.randn_like(out), lse, 4, 0.1, 5)
     q2 = torch.randn(256, 8, 512, device="cuda")
     k2, v2 = (torch.randn(2048, 8, 512, device="cuda") for _ in range(2))
-    attention_launch.forward(q2, k2, v2, 4)           # decoder cross-attention, 256 x 2048, 4 x 128
+    out2, lse2 = attention_launch.forward(q2, k2, v2, 4, dropout_p=0.1, salt=6)  # decoder cross-attention, 256 x 2048, 4 x 128
+    attention_launch.backward(q2, k2, v2, out2, torch.randn_like(out2), lse2, 4, 0.1, 6)
+    qc = torch.randn(50, 256, 768, device="cuda")
+    attention_launch.forward(qc, qc, qc, 12, nsplit=2)                           # CLIP image tower, 50 tokens, 12 x 64
 if which in ("fps", "all"):
     xyz = torch.from_numpy(synthetic.point_clouds(8, 20000, seed=0)).cuda()
     for _ in range(2):
@@ -29,5 +33,23 @@ if which in ("gemm", "all"):
     w = torch.randn(512, 512, device="cuda")
     for _ in range(2):
         ops.linear(a, w)
+    # the longest GEMM launch of the step: SA layer 3, (B * npoint * nsample = 1M rows) x 128 -> 256, HBM-bound
+    rows = 8 * 2048 * 64
+    ap = torch.randn(3, 1, rows, 128, device="cuda").bfloat16()
+    wp = ops.pack_split(torch.randn(256, 128, device="cuda"), 256, 128, 128, 1, 3)
+    y = torch.empty(1, rows, 256, device="cuda")
+    for _ in range(2):
+        ops.gemm_nt(ap, wp, rows, 256, out=y)
+    # CLIP MLP c_fc: fp16 operands and output, QuickGELU epilogue
+    xh = (torch.randn(1, 1, 12800, 768, device="cuda") * 0.1).half()
+    wh = (torch.randn(1, 1, 3072, 768, device="cuda") * 0.1).half()
+    for _ in range(2):
+        ops.gemm_nt(xh, wh, 12800, 3072, bias=torch.zeros(3072, device="cuda"), act=2, out_dtype=torch.float16)
+if which in ("sa", "all"):
+    from coda_neurips2023_b200.pointnet2 import pytorch_utils as pt_utils
+    mlp = pt_utils.SharedMLP([3, 64, 128, 256], bn=True).cuda().train()
+    x = torch.randn(8, 3, 2048, 64, device="cuda")
+    for _ in range(2):
+        mlp.forward_max_pooled(x).sum().backward()
 torch.cuda.synchronize()
 print("done")
