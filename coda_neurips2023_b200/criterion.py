@@ -116,11 +116,20 @@ class SetCriterion(nn.Module):
         return fn
 
     # ------------------------------------------------------------------ losses
+    # Every loss works on N = L * B "scenes": the L decoder layers handled in this call stacked along the batch
+    # axis (layer-major), with the targets repeated L times.  A loss returns one value per layer, shape (L,):
+    # per-scene sums are reduced layer by layer (`_by_layer`), never across layers.  L = 1 is the plain
+    # per-output call of the reference (criterion.py:1092-1175); the seven auxiliary outputs of the decoder go
+    # through ONE call with L = 7 instead of seven, which divides the criterion's kernel launches by four.
+    def _by_layer(self, per_scene):
+        return per_scene.reshape(self._nlayers, -1).sum(dim=1)
+
     @torch.no_grad()
     def loss_cardinality(self, outputs, targets, assignments):
         pred_logits = outputs["sem_cls_logits"]
         pred_objects = (pred_logits.argmax(-1) != pred_logits.shape[-1] - 1).sum(1)
-        return {"loss_cardinality": F.l1_loss(pred_objects.float(), targets["nactual_gt"])}
+        err = (pred_objects.float() - targets["nactual_gt"]).abs()
+        return {"loss_cardinality": self._by_layer(err) / (err.shape[0] // self._nlayers)}
 
     def _matched_cls_labels(self, outputs, targets, assignments):
         pred_logits = outputs["sem_cls_logits"]
@@ -130,8 +139,9 @@ class SetCriterion(nn.Module):
 
     def loss_sem_cls_softmax(self, outputs, targets, assignments):
         pred_logits, gt_box_label = self._matched_cls_labels(outputs, targets, assignments)
-        loss = F.cross_entropy(pred_logits.transpose(2, 1), gt_box_label, self.semcls_percls_weights,
-                               reduction="mean")
+        # weighted mean of F.cross_entropy(weight=w, reduction="mean") = sum(w[y] * nll) / sum(w[y]), per layer
+        wnll = F.cross_entropy(pred_logits.transpose(2, 1), gt_box_label, self.semcls_percls_weights, reduction="none")
+        loss = self._by_layer(wnll.sum(dim=1)) / self._by_layer(self.semcls_percls_weights[gt_box_label].sum(dim=1))
         if self.if_skip_no_seen_scene_objectness:
             loss = loss * (targets["num_boxes_replica"] > 0).to(loss.dtype)
         return {"loss_sem_cls_softmax": loss}
@@ -142,7 +152,7 @@ class SetCriterion(nn.Module):
         loss = F.cross_entropy(pred_logits.transpose(2, 1), gt_box_label, self.semcls_percls_weights,
                                reduction="none")
         has_obj = (targets["gt_box_present"].sum(dim=1) != 0).to(loss.dtype)
-        final = (loss.sum(dim=1) * has_obj).sum() / (has_obj.sum() * loss.shape[1] + 1e-32)
+        final = self._by_layer(loss.sum(dim=1) * has_obj) / (self._by_layer(has_obj) * loss.shape[1] + 1e-32)
         return {"loss_sem_cls_softmax_skip_none_gt_sample": final}
 
     def loss_angle(self, outputs, targets, assignments):
@@ -153,23 +163,24 @@ class SetCriterion(nn.Module):
         inds, mask = assignments["per_prop_gt_inds"], assignments["proposal_matched_mask"]
         gt_angle_label = torch.gather(targets["gt_angle_class_label"], 1, inds)
         gt_res_norm = targets["gt_angle_residual_label"] / (np.pi / self.dataset_config.num_angle_bin)
-        angle_cls_loss = (F.cross_entropy(angle_logits.transpose(2, 1), gt_angle_label, reduction="none") * mask).sum()
+        angle_cls_loss = self._by_layer(
+            (F.cross_entropy(angle_logits.transpose(2, 1), gt_angle_label, reduction="none") * mask).sum(dim=1))
         gt_res_norm = torch.gather(gt_res_norm, 1, inds)
         res_for_gt_class = torch.gather(angle_residual, 2, gt_angle_label.unsqueeze(-1)).squeeze(-1)
-        angle_reg_loss = (huber_loss(res_for_gt_class - gt_res_norm, delta=1.0) * mask).sum()
+        angle_reg_loss = self._by_layer((huber_loss(res_for_gt_class - gt_res_norm, delta=1.0) * mask).sum(dim=1))
         return {"loss_angle_cls": angle_cls_loss / targets["num_boxes"],
                 "loss_angle_reg": angle_reg_loss / targets["num_boxes"]}
 
     def loss_center(self, outputs, targets, assignments):
         center_dist = outputs["center_dist"]
         center_loss = torch.gather(center_dist, 2, assignments["per_prop_gt_inds"].unsqueeze(-1)).squeeze(-1)
-        center_loss = (center_loss * assignments["proposal_matched_mask"]).sum()
+        center_loss = self._by_layer((center_loss * assignments["proposal_matched_mask"]).sum(dim=1))
         return {"loss_center": center_loss / targets["num_boxes"]}
 
     def loss_giou(self, outputs, targets, assignments):
         gious_dist = 1 - outputs["gious"]
         giou_loss = torch.gather(gious_dist, 2, assignments["per_prop_gt_inds"].unsqueeze(-1)).squeeze(-1)
-        giou_loss = (giou_loss * assignments["proposal_matched_mask"]).sum()
+        giou_loss = self._by_layer((giou_loss * assignments["proposal_matched_mask"]).sum(dim=1))
         return {"loss_giou": giou_loss / targets["num_boxes"]}
 
     def loss_size(self, outputs, targets, assignments):
@@ -178,17 +189,20 @@ class SetCriterion(nn.Module):
         inds = assignments["per_prop_gt_inds"].unsqueeze(-1).expand(-1, -1, gt_box_sizes.shape[-1])
         gt = torch.gather(gt_box_sizes, 1, inds)
         size_loss = F.l1_loss(pred_box_sizes, gt, reduction="none").sum(dim=-1)
-        size_loss = (size_loss * assignments["proposal_matched_mask"]).sum()
+        size_loss = self._by_layer((size_loss * assignments["proposal_matched_mask"]).sum(dim=1))
         return {"loss_size": size_loss / targets["num_boxes"]}
 
     def loss_predicted_region_embed_l1(self, outputs, targets, assignments):
         """The cross-modal alignment loss: masked L1 between the 512-d head output and the
-        CLIP embedding of the box's image crop (reference :924-943)."""
-        target = targets["gt_text_correlation_embedding"]
-        pred = outputs["text_correlation_embedding"]
+        CLIP embedding of the box's image crop (reference :924-943).  The (B, Q, 512) target is broadcast
+        over the layer axis rather than repeated."""
+        target = targets["gt_text_correlation_embedding"]           # (B, Q, D): NOT repeated per layer
         w = targets["gt_text_correlation_embedding_mask"]
-        ave_weight = torch.sum(w) * pred.shape[2]
-        return {"loss_predicted_region_embed_l1": F.l1_loss(pred * w, target * w, reduction="sum") / ave_weight}
+        pred = outputs["text_correlation_embedding"]
+        pred = pred.reshape(self._nlayers, *target.shape)
+        ave_weight = torch.sum(w) * pred.shape[-1]
+        diff = (pred * w - target * w).abs()
+        return {"loss_predicted_region_embed_l1": diff.sum(dim=(1, 2, 3)) / ave_weight}
 
     def loss_feat_seen_softmax_weakly_loss_with_novel_cate_confi(self, outputs, targets, assignments):
         """The contrastive loss of stage 2: CE over logit_scale * cos(head embedding, text
@@ -208,16 +222,34 @@ class SetCriterion(nn.Module):
         elif self.confidence_type != "clip-max-prob":
             raise NotImplementedError(f"confidence_type={self.confidence_type}")
         loss = F.cross_entropy(corr.transpose(2, 1), label, reduction="none")
-        all_num = torch.sum(conf > 1e-32) + 1e-32
-        return {"loss_feat_seen_softmax_weakly_loss_with_novel_cate_confi": torch.sum(loss * conf) / all_num}
+        all_num = self._by_layer((conf > 1e-32).sum(dim=1)) + 1e-32
+        return {"loss_feat_seen_softmax_weakly_loss_with_novel_cate_confi":
+                self._by_layer((loss * conf).sum(dim=1)) / all_num}
 
     # ------------------------------------------------------------------ driver
     _LAST_HEAD_ONLY = ("loss_contrast_3dto2d_text_weight", "loss_3d_2d_region_embed_weight",
                        "loss_predicted_region_embed_l1_only_last_layer_weight")
     _SKIP_IN_AUX = ("loss_contrastive", "loss_image_seen_class", "loss_batchwise_contrastive",
                     "loss_3d_2d_region_embed", "loss_predicted_region_embed_l1_only_last_layer")
+    # per-scene targets that are repeated along the stacked layer axis (everything the losses index by scene,
+    # except the (B, Q, 512) alignment target, which is broadcast)
+    _PER_SCENE = ("gt_box_sem_cls_label", "gt_box_centers_normalized", "gt_box_corners", "nactual_gt",
+                  "gt_angle_class_label", "gt_angle_residual_label", "gt_box_sizes_normalized", "gt_box_present",
+                  "gt_box_seen_sem_cls_label", "gt_box_seen_sem_cls_confi", "text_features_clip",
+                  "weak_box_cate_label", "weak_confidence_weight", "gt_box_angles")
 
-    def single_output_forward(self, outputs, targets, if_region_embed=False, if_aux=False, if_last_head=False):
+    def single_output_forward(self, outputs, targets, if_region_embed=False, if_aux=False, if_last_head=False,
+                              nlayers: int = 1):
+        """`outputs` holds `nlayers` decoder layers stacked along the batch axis (layer-major).  Returns
+        (sum over these layers of the weighted loss, {name: (nlayers,) weighted per-layer values})."""
+        self._nlayers = nlayers
+        if nlayers > 1:
+            rep = dict(targets)
+            for k in self._PER_SCENE:
+                if isinstance(targets.get(k), torch.Tensor):
+                    t = targets[k]
+                    rep[k] = t.repeat(nlayers, *([1] * (t.dim() - 1)))
+            targets = rep
         outputs["gious"] = generalized_box3d_iou(
             outputs["box_corners"], targets["gt_box_corners"], targets["nactual_gt"],
             rotated_boxes=targets["_rotated_flag"], needs_grad=(self.loss_weight_dict["loss_giou_weight"] > 0),
@@ -248,7 +280,7 @@ class SetCriterion(nn.Module):
                     continue
                 name = k.replace("_weight", "")
                 losses[name] = losses[name] * w
-                final_loss = final_loss + losses[name]
+                final_loss = final_loss + losses[name].sum()
         return final_loss, losses
 
     def forward(self, outputs, targets):
@@ -266,14 +298,27 @@ class SetCriterion(nn.Module):
             if key in out:
                 targets[key] = out[key]
 
-        loss, loss_dict = self.single_output_forward(out, targets, if_region_embed=False, if_last_head=True)
-        if "aux_outputs" in outputs:
-            for k, aux in enumerate(outputs["aux_outputs"]):
-                interm_loss, interm_loss_dict = self.single_output_forward(
-                    aux, targets, if_region_embed=False, if_aux=True, if_last_head=False)
+        loss, per_layer = self.single_output_forward(out, targets, if_region_embed=False, if_last_head=True)
+        loss_dict = {k: v[0] for k, v in per_layer.items()}
+        aux = outputs.get("aux_outputs") or []
+        stacked = outputs.get("stacked_layers")
+        if aux and stacked is not None:
+            # our model: the decoder layers are slices of (L, B, ...) tensors -- all auxiliary layers in one call
+            na = len(aux)
+            flat = {k: v[:na].reshape(na * v.shape[1], *v.shape[2:]) for k, v in stacked.items()}
+            interm_loss, interm = self.single_output_forward(flat, targets, if_region_embed=False, if_aux=True,
+                                                             if_last_head=False, nlayers=na)
+            loss = loss + interm_loss
+            for key, val in interm.items():
+                for k in range(na):
+                    loss_dict[f"{key}_{k}"] = val[k]
+        else:
+            for k, a in enumerate(aux):
+                interm_loss, interm = self.single_output_forward(a, targets, if_region_embed=False, if_aux=True,
+                                                                 if_last_head=False)
                 loss = loss + interm_loss
-                for key, val in interm_loss_dict.items():
-                    loss_dict[f"{key}_{k}"] = val
+                for key, val in interm.items():
+                    loss_dict[f"{key}_{k}"] = val[0]
         return loss, loss_dict
 
 

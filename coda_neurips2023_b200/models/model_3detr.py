@@ -317,36 +317,45 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
         angle_residual_normalized = head("angle_residual_head")
         angle_residual = angle_residual_normalized * (np.pi / angle_residual_normalized.shape[-1])
 
+        # box decoding for ALL decoder layers at once: (layer, batch) is one flat batch axis of N = L * B scenes
+        n = num_layers * batch
+        flat = lambda t: t.reshape(n, num_queries, t.shape[-1])  # noqa: E731
+        q_rep = query_xyz.repeat(num_layers, 1, 1)
+        dims_rep = [d.repeat(num_layers, 1) for d in point_cloud_dims]
+        center_normalized, center_unnormalized = self.box_processor.compute_predicted_center(
+            flat(center_offset), q_rep, dims_rep)
+        angle_continuous = self.box_processor.compute_predicted_angle(flat(angle_logits), flat(angle_residual))
+        size_unnormalized = self.box_processor.compute_predicted_size(flat(size_normalized), dims_rep)
+        box_corners = self.box_processor.box_parametrization_to_corners(
+            center_unnormalized, size_unnormalized, angle_continuous)
+        box_corners_xyz = self.box_processor.box_parametrization_to_corners_xyz(
+            center_unnormalized, size_unnormalized, angle_continuous)
+        with torch.no_grad():
+            semcls_prob, objectness_prob = self.box_processor.compute_objectness_and_cls_prob(flat(cls_logits))
+        lay = lambda t: t.reshape(num_layers, batch, *t.shape[1:])  # noqa: E731
+        stacked = {
+            "sem_cls_logits": cls_logits,
+            "text_correlation_embedding": text_correlation_embedding,
+            "center_normalized": lay(center_normalized.contiguous()),
+            "center_unnormalized": lay(center_unnormalized),
+            "size_normalized": size_normalized,
+            "size_unnormalized": lay(size_unnormalized),
+            "angle_logits": angle_logits,
+            "angle_residual": angle_residual,
+            "angle_residual_normalized": angle_residual_normalized,
+            "angle_continuous": lay(angle_continuous),
+            "objectness_prob": lay(objectness_prob),
+            "sem_cls_prob": lay(semcls_prob),
+            "box_corners": lay(box_corners),
+            "box_corners_xyz": lay(box_corners_xyz),
+        }
         outputs = []
-        for l in range(num_layers):
-            center_normalized, center_unnormalized = self.box_processor.compute_predicted_center(
-                center_offset[l], query_xyz, point_cloud_dims)
-            angle_continuous = self.box_processor.compute_predicted_angle(angle_logits[l], angle_residual[l])
-            size_unnormalized = self.box_processor.compute_predicted_size(size_normalized[l], point_cloud_dims)
-            box_corners = self.box_processor.box_parametrization_to_corners(
-                center_unnormalized, size_unnormalized, angle_continuous)
-            box_corners_xyz = self.box_processor.box_parametrization_to_corners_xyz(
-                center_unnormalized, size_unnormalized, angle_continuous)
-            with torch.no_grad():
-                semcls_prob, objectness_prob = self.box_processor.compute_objectness_and_cls_prob(cls_logits[l])
-            outputs.append({
-                "sem_cls_logits": cls_logits[l],
-                "text_correlation_embedding": text_correlation_embedding[l],
-                "center_normalized": center_normalized.contiguous(),
-                "center_unnormalized": center_unnormalized,
-                "size_normalized": size_normalized[l],
-                "size_unnormalized": size_unnormalized,
-                "angle_logits": angle_logits[l],
-                "angle_residual": angle_residual[l],
-                "angle_residual_normalized": angle_residual_normalized[l],
-                "angle_continuous": angle_continuous,
-                "objectness_prob": objectness_prob,
-                "sem_cls_prob": semcls_prob,
-                "box_corners": box_corners,
-                "box_corners_xyz": box_corners_xyz,
-                "point_clouds": point_clouds,
-            })
-        return {"outputs": outputs[-1], "aux_outputs": outputs[:-1]}
+        for l in range(num_layers):   # the reference's per-layer dicts are views into the stacked tensors
+            d = {k: v[l] for k, v in stacked.items()}
+            d["point_clouds"] = point_clouds
+            outputs.append(d)
+        # "stacked_layers" lets the criterion take every auxiliary layer in one call (criterion.SetCriterion.forward)
+        return {"outputs": outputs[-1], "aux_outputs": outputs[:-1], "stacked_layers": stacked}
 
     # ------------------------------------------------------------------ CLIP crops
     def draw_box_selection(self, bsz: int) -> np.ndarray:
