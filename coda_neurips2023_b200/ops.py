@@ -382,13 +382,15 @@ _BIAS32: dict = {}
 
 
 def _bias_fp32(bias):
-    """fp32 copy of a (frozen, fp16) bias, cached: the epilogue adds the bias in fp32."""
-    key = (bias.data_ptr(), bias._version)
-    if key not in _BIAS32:
+    """fp32 copy of a (frozen, fp16) bias, cached: the epilogue adds the bias in fp32.  The entry keeps the
+    source tensor alive so that its address cannot be recycled for another parameter while the entry exists."""
+    key = (bias.data_ptr(), tuple(bias.shape), bias._version)
+    hit = _BIAS32.get(key)
+    if hit is None:
         if len(_BIAS32) > 256:
             _BIAS32.clear()
-        _BIAS32[key] = bias.detach().float()
-    return _BIAS32[key]
+        hit = _BIAS32[key] = (bias.detach().float(), bias)
+    return hit[0]
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool = False, nsplit: int | None = None,
