@@ -150,6 +150,27 @@ __global__ void bn_stats_finalize_kernel(int nblocks, long long rows, int c, con
   if (running_var) running_var[ch] = (1.0f - momentum) * running_var[ch] + momentum * (float)(var * (n / fmax(n - 1.0, 1.0)));
 }
 
+// column sums only (bias gradients: db = sum over rows of dY); partial[blk][c]
+__global__ void __launch_bounds__(THREADS)
+colsum_partial_kernel(long long rows, int c, const float *__restrict__ x, float *__restrict__ partial) {
+  __shared__ float4 red[THREADS];
+  const int cq = c >> 2, c4 = threadIdx.x % cq, slot = threadIdx.x / cq, nslots = THREADS / cq;
+  float4 acc[1] = {make_float4(0.f, 0.f, 0.f, 0.f)};
+  for (long long r = (long long)blockIdx.x * nslots + slot; r < rows; r += (long long)gridDim.x * nslots) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * c) + c4);
+    acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+  }
+  reduce_slots<1>(acc, cq, slot, c4, red);
+  if (slot == 0) reinterpret_cast<float4 *>(partial + (size_t)blockIdx.x * c)[c4] = acc[0];
+}
+__global__ void colsum_finalize_kernel(int nblocks, int c, const float *__restrict__ partial, float *__restrict__ out) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double a = 0.0;
+  for (int k = 0; k < nblocks; ++k) a += (double)partial[(size_t)k * c + ch];
+  out[ch] = (float)a;
+}
+
 // ------------------------------------------------------------------ forward: normalise + ReLU + operand planes
 template <int NS>
 __global__ void __launch_bounds__(THREADS)
@@ -398,6 +419,17 @@ int coda_bn_rows_stats(long long rows, int c, const float *y, float eps, float m
   bn_stats_partial_kernel<<<grid, THREADS, 0, s>>>(rows, c, y, scratch);
   bn_stats_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>((int)grid, rows, c, scratch, eps, momentum, running_mean,
                                                            running_var, mean, invstd);
+  return coda::launch_status();
+}
+
+int coda_rows_colsum(long long rows, int c, const float *x, float *out, float *scratch, void *stream) {
+  if (rows <= 0 || !channels_ok(c) || !x || !out || !scratch) return CODA_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  // short matrices: fewer blocks keep the second stage short
+  unsigned grid = grid_for(rows, c);
+  if (grid > 148) grid = 148;
+  colsum_partial_kernel<<<grid, THREADS, 0, s>>>(rows, c, x, scratch);
+  colsum_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>((int)grid, c, scratch, out);
   return coda::launch_status();
 }
 

@@ -332,6 +332,21 @@ def _packed_weight(w: torch.Tensor, transposed: bool, nsplit: int) -> torch.Tens
     return hit[0]
 
 
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """sum over the rows of a contiguous (rows, c) fp32 matrix (bias gradients); falls back to torch for channel
+    counts the row kernels do not cover."""
+    rows, c = x.shape
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and rows > 0
+            and 4 <= c <= 1024 and c % 4 == 0 and 256 % (c // 4) == 0):
+        return x.sum(dim=0)
+    out = torch.empty(c, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(148 * 4 * 2 * c, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        st = lib().coda_rows_colsum(_ll(rows), _i(c), ptr(x), ptr(out), ptr(scratch), stream_of(x))
+    check(st, "rows_colsum")
+    return out
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, relu, nsplit):
@@ -374,7 +389,7 @@ class _Linear(torch.autograd.Function):
                 xt = pack_split(x, k, m, 1, x.stride(0), nsplit)
                 dw = gemm_nt(dyt, xt, n, k)[0]
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(dim=0)
+            db = colsum(dy)
         return dx, dw, db, None, None
 
 

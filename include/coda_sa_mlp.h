@@ -45,6 +45,12 @@ int coda_bn_rows_stats(long long rows, int c, const float *y, float eps, float m
                        float *running_var, float *mean, float *invstd, float *scratch, void *stream);
 
 /*
+ * out[c] = sum over rows of x (rows, c): the bias gradient of a Linear (db = column sums of dY); deterministic
+ * two-stage reduction; scratch as for coda_bn_rows_stats.   replaces `dy.sum(dim=0)` in the Linear backward.
+ */
+int coda_rows_colsum(long long rows, int c, const float *x, float *out, float *scratch, void *stream);
+
+/*
  * planes = split_bf16( relu( (y - mean) * invstd * gamma + beta ) ): bf16 [nsplit][rows][c], the A operand of
  * the next coda_gemm_nt (and the row operand of coda_gemm_tn for its weight gradient).
  */
