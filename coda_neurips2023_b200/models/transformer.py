@@ -132,7 +132,7 @@ class TransformerEncoderLayer(nn.Module):
         src = src + self.dropout1(attn)
         if self.use_ffn:
             src2 = self.norm2(src)
-            src2 = self.linear2(self.dropout(self.activation(self.linear1(src2))))
+            src2 = self.linear2(self.dropout(_ffn_hidden(self, src2)))
             src = src + self.dropout2(src2)
         if return_attn_weights:
             return src, None
@@ -144,7 +144,7 @@ class TransformerEncoderLayer(nn.Module):
         src = src + self.dropout1(src2)
         src = self.norm1(src)
         if self.use_ffn:
-            src2 = self.linear2(self.dropout(self.activation(self.linear1(src))))
+            src2 = self.linear2(self.dropout(_ffn_hidden(self, src)))
             src = self.norm2(src + self.dropout2(src2))
         return src
 
@@ -209,6 +209,14 @@ class TransformerDecoder(nn.Module):
         return output, []
 
 
+def _ffn_hidden(layer, x):
+    """activation(linear1(x)); with a ReLU activation the rectifier runs in the GEMM epilogue (one kernel less
+    forward and backward)."""
+    if isinstance(layer.activation, nn.ReLU):
+        return ops.linear(x, layer.linear1.weight, layer.linear1.bias, relu=True)
+    return layer.activation(layer.linear1(x))
+
+
 class TransformerDecoderLayer(nn.Module):
     def __init__(self, d_model, nhead=4, dim_feedforward=256, dropout=0.1, dropout_attn=None,
                  activation="relu", normalize_before=True, norm_fn_name="ln"):
@@ -246,7 +254,7 @@ class TransformerDecoderLayer(nn.Module):
                                    attn_mask=memory_mask, key_padding_mask=memory_key_padding_mask)[0]
         tgt = tgt + self.dropout2(tgt2)
         tgt2 = self.norm3(tgt)
-        tgt2 = self.linear2(self.dropout(self.activation(self.linear1(tgt2))))
+        tgt2 = self.linear2(self.dropout(_ffn_hidden(self, tgt2)))
         tgt = tgt + self.dropout3(tgt2)
         return tgt, None
 
@@ -261,7 +269,7 @@ class TransformerDecoderLayer(nn.Module):
         tgt2 = self.multihead_attn(self.with_pos_embed(tgt, query_pos), memory_key, memory,
                                    attn_mask=memory_mask, key_padding_mask=memory_key_padding_mask)[0]
         tgt = self.norm2(tgt + self.dropout2(tgt2))
-        tgt2 = self.linear2(self.dropout(self.activation(self.linear1(tgt))))
+        tgt2 = self.linear2(self.dropout(_ffn_hidden(self, tgt)))
         tgt = self.norm3(tgt + self.dropout3(tgt2))
         return tgt, None
 
