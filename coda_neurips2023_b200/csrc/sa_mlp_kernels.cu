@@ -163,12 +163,16 @@ colsum_partial_kernel(long long rows, int c, const float *__restrict__ x, float 
   reduce_slots<1>(acc, cq, slot, c4, red);
   if (slot == 0) reinterpret_cast<float4 *>(partial + (size_t)blockIdx.x * c)[c4] = acc[0];
 }
-__global__ void colsum_finalize_kernel(int nblocks, int c, const float *__restrict__ partial, float *__restrict__ out) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel: lanes stride over the block partials, then a shuffle tree
+__global__ void __launch_bounds__(256)
+colsum_finalize_kernel(int nblocks, int c, const float *__restrict__ partial, float *__restrict__ out) {
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (ch >= c) return;
-  double a = 0.0;
-  for (int k = 0; k < nblocks; ++k) a += (double)partial[(size_t)k * c + ch];
-  out[ch] = (float)a;
+  float a = 0.f;
+  for (int k = lane; k < nblocks; k += 32) a += partial[(size_t)k * c + ch];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[ch] = a;
 }
 
 // ------------------------------------------------------------------ forward: normalise + ReLU + operand planes
@@ -429,7 +433,7 @@ int coda_rows_colsum(long long rows, int c, const float *x, float *out, float *s
   unsigned grid = grid_for(rows, c);
   if (grid > 148) grid = 148;
   colsum_partial_kernel<<<grid, THREADS, 0, s>>>(rows, c, x, scratch);
-  colsum_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>((int)grid, c, scratch, out);
+  colsum_finalize_kernel<<<(c + 7) / 8, 256, 0, s>>>((int)grid, c, scratch, out);
   return coda::launch_status();
 }
 
