@@ -32,25 +32,43 @@ def next_salt() -> int:
     return _CALL_SALT
 
 
+def _row_strided(t: torch.Tensor):
+    """(L, B, E) view whose (l, b) rows are `ld` elements apart (a slice of a wider projection) -> ld, else None"""
+    l, b, e = t.shape
+    if t.stride(2) == 1 and t.stride(0) == b * t.stride(1) and t.stride(1) >= e and t.stride(1) % 4 == 0:
+        return t.stride(1)
+    return None
+
+
 def forward(q, k, v, nhead: int, dropout_p: float = 0.0, salt: int = 0, nsplit: int = 3):
-    """q (Lq, B, E), k / v (Lk, B, E) fp32 contiguous -> (out (Lq, B, E), lse (B*H, Lq))."""
+    """q (Lq, B, E), k / v (Lk, B, E), fp32 or fp16 (all three alike), each either contiguous or a row-strided
+    slice of a fused projection -> (out (Lq, B, E) fp32, lse (B*H, Lq))."""
     lq, b, e = q.shape
     lk = k.shape[0]
     hd = e // nhead
     assert hd in (64, 128), "head dim must be 64 or 128"
-    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
-    out = torch.empty_like(q)
+    is_half = q.dtype == torch.float16
+    assert k.dtype == q.dtype and v.dtype == q.dtype and q.dtype in (torch.float16, torch.float32)
+    lds = [_row_strided(t) for t in (q, k, v)]
+    if any(ld is None for ld in lds):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        lds = [e, e, e]
+    out = torch.empty((lq, b, e), dtype=torch.float32, device=q.device)
     lse = torch.empty((b * nhead, lq), dtype=torch.float32, device=q.device)
     L = lib()
     L.coda_attention_workspace_bytes.restype = ctypes.c_longlong
     ws_bytes = L.coda_attention_workspace_bytes(b, nhead, lq, lk, hd, nsplit)
     ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=q.device)
     seed_dev = seed_counter(q.device) if dropout_p > 0.0 else None
+    ci, cl = ctypes.c_int, ctypes.c_longlong
     with torch.cuda.device(q.device):
-        st = L.coda_attention_fwd(ctypes.c_int(b), ctypes.c_int(nhead), ctypes.c_int(lq), ctypes.c_int(lk),
-                                  ctypes.c_int(hd), ctypes.c_int(nsplit), ctypes.c_float(float(hd) ** -0.5), ptr(q),
-                                  ptr(k), ptr(v), ptr(out), ptr(lse), ctypes.c_float(dropout_p),
-                                  ctypes.c_uint(salt & 0xFFFFFFFF), ptr(seed_dev), ptr(ws), stream_of(q))
+        st = L.coda_attention_pack_strided(ci(b), ci(nhead), ci(lq), ci(lk), ci(hd), ci(nsplit),
+                                           ctypes.c_float(float(hd) ** -0.5), ptr(q), ptr(k), ptr(v), cl(lds[0]),
+                                           cl(lds[1]), cl(lds[2]), ci(1 if is_half else 0), ptr(ws), stream_of(q))
+        check(st, "attention_pack")
+        st = L.coda_attention_fwd_packed(ci(b), ci(nhead), ci(lq), ci(lk), ci(hd), ci(nsplit), ptr(ws), ptr(out),
+                                         ptr(lse), ctypes.c_float(dropout_p), ctypes.c_uint(salt & 0xFFFFFFFF),
+                                         ptr(seed_dev), stream_of(q))
     check(st, "attention_fwd")
     return out, lse
 

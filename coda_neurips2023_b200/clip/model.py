@@ -70,7 +70,8 @@ class _PackedSelfAttention(nn.Module):
         if x.is_cuda and x.dtype == torch.float16 and not causal and self.embed_dim // self.num_heads == 64:
             # image tower: fused tcgen05 attention on 2 bf16 planes (16 mantissa bits >= fp16's 11)
             from .. import attention_launch
-            out = attention_launch.forward(q.float(), k.float(), v.float(), self.num_heads, nsplit=2)[0].to(x.dtype)
+            # q / k / v stay fp16 slices of the fused projection: the pack kernel reads them in place
+            out = attention_launch.forward(q, k, v, self.num_heads, nsplit=2)[0].to(x.dtype)
         else:
             out = ops.attention(q, k, v, self.num_heads, 0.0, False, causal=causal)
         return _linear(out, self.out_proj.weight, self.out_proj.bias)

@@ -541,12 +541,13 @@ int coda_attention_bwd(int b, int h, int lq, int lk, int hd, float scale, const 
   float *delta = (float *)(((uintptr_t)w + 255) & ~(uintptr_t)255);
   if ((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)dout) & 15) != 0) return CODA_EINVAL;
   PackJobs jobs = {};
-  jobs.job[0] = {q, qp, lq, scale};
-  jobs.job[1] = {dout, dop, lq, 1.0f};
-  jobs.job[2] = {k, kp, lk, 1.0f};
-  jobs.job[3] = {v, vp, lk, 1.0f};
+  const long long e = (long long)h * hd;
+  jobs.job[0] = {q, qp, lq, scale, e};
+  jobs.job[1] = {dout, dop, lq, 1.0f, e};
+  jobs.job[2] = {k, kp, lk, 1.0f, e};
+  jobs.job[3] = {v, vp, lk, 1.0f, e};
   const long long t4 = (long long)(lq > lk ? lq : lk) * bh * hd / 4;
-  pack_rows_multi_kernel<NS><<<dim3((unsigned)((t4 + 255) / 256), 4), 256, 0, s>>>(jobs, b, h, hd);
+  pack_rows_multi_kernel<NS, false><<<dim3((unsigned)((t4 + 255) / 256), 4), 256, 0, s>>>(jobs, b, h, hd);
   bwd_delta_kernel<<<(unsigned)(((long long)lq * bh * 32 + 255) / 256), 256, 0, s>>>(lq, b, h, hd, dout, out, delta);
   int st = launch_status();
   if (st != CODA_OK) return st;

@@ -36,18 +36,20 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16 *dst, size_t plane
   }
 }
 
-// Several (L, B, H*hd) fp32 tensors -> row planes [NS][B*H][L][hd] in ONE launch: blockIdx.y selects the
-// tensor, a thread converts four consecutive head-dim elements (16-byte load, 8-byte store per plane).
+// Several (L, B, H*hd) tensors (fp32 or fp16, row stride `ld` elements: slices of a fused qkv projection are
+// read in place) -> row planes [NS][B*H][L][hd] in ONE launch: blockIdx.y selects the tensor, a thread converts
+// four consecutive head-dim elements (one 16- or 8-byte load, one 8-byte store per plane).
 struct PackJob {
-  const float *src;
+  const void *src;
   __nv_bfloat16 *planes;
   int L;
   float scale;
+  long long ld;     // elements between consecutive (l, b) rows of src
 };
 struct PackJobs {
   PackJob job[4];
 };
-template <int NSPLIT>
+template <int NSPLIT, bool HALF_IN>
 __global__ void __launch_bounds__(256)
 pack_rows_multi_kernel(const __grid_constant__ PackJobs jobs, int B, int H, int hd) {
   const PackJob jb = jobs.job[blockIdx.y];
@@ -57,11 +59,20 @@ pack_rows_multi_kernel(const __grid_constant__ PackJobs jobs, int B, int H, int 
   const int hd4 = hd >> 2;
   const int d = (int)(i4 % hd4) * 4;
   long long t = i4 / hd4;
-  const int h = (int)(t % H); t /= H;
+  const int h = (int)(t % H); t /= H;     // t = l * B + b
   const int b = (int)(t % B);
   const int l = (int)(t / B);
-  const float4 v = __ldg(reinterpret_cast<const float4 *>(jb.src) + i4);
-  float r[4] = {v.x * jb.scale, v.y * jb.scale, v.z * jb.scale, v.w * jb.scale};
+  const long long off = t * jb.ld + (long long)h * hd + d;
+  float r[4];
+  if (HALF_IN) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(static_cast<const __half *>(jb.src) + off));
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+    r[0] = lo.x * jb.scale; r[1] = lo.y * jb.scale; r[2] = hi.x * jb.scale; r[3] = hi.y * jb.scale;
+  } else {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(static_cast<const float *>(jb.src) + off));
+    r[0] = v.x * jb.scale; r[1] = v.y * jb.scale; r[2] = v.z * jb.scale; r[3] = v.w * jb.scale;
+  }
   __nv_bfloat16 *dst = jb.planes + (((size_t)(b * H + h)) * jb.L + l) * hd + d;
   const size_t plane_stride = (size_t)total4 * 4;
 #pragma unroll

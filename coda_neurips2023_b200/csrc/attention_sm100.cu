@@ -442,13 +442,16 @@ static int attn_check(int b, int h, int lq, int lk, int hd, int nsplit) {
   return CODA_OK;
 }
 
-int coda_attention_pack(int b, int h, int lq, int lk, int hd, int nsplit, float scale, const float *q,
-                        const float *k, const float *v, void *workspace, void *stream) {
+int coda_attention_pack_strided(int b, int h, int lq, int lk, int hd, int nsplit, float scale, const void *q,
+                                const void *k, const void *v, long long ld_q, long long ld_k, long long ld_v,
+                                int is_half, void *workspace, void *stream) {
   int st = attn_check(b, h, lq, lk, hd, nsplit);
   if (st != CODA_OK) return st;
   if (b == 0 || lq == 0) return CODA_OK;
   if (!q || !k || !v || !workspace) return CODA_EINVAL;
-  if ((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) != 0) return CODA_EINVAL;
+  const uintptr_t amask = is_half ? 7 : 15;    // four elements per load
+  if ((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & amask) != 0 || ((ld_q | ld_k | ld_v) & 3) != 0) return CODA_EINVAL;
+  if (ld_q < (long long)h * hd || ld_k < (long long)h * hd || ld_v < (long long)h * hd) return CODA_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   const int bh = b * h;
   __nv_bfloat16 *qp = (__nv_bfloat16 *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -456,15 +459,23 @@ int coda_attention_pack(int b, int h, int lq, int lk, int hd, int nsplit, float 
   __nv_bfloat16 *vp = kp + (size_t)nsplit * bh * lk * hd;
   // q carries scale * log2(e): the kernel's softmax works in base 2.  All three tensors in one launch.
   PackJobs jobs = {};
-  jobs.job[0] = {q, qp, lq, scale * LOG2E};
-  jobs.job[1] = {k, kp, lk, 1.0f};
-  jobs.job[2] = {v, vp, lk, 1.0f};
+  jobs.job[0] = {q, qp, lq, scale * LOG2E, ld_q};
+  jobs.job[1] = {k, kp, lk, 1.0f, ld_k};
+  jobs.job[2] = {v, vp, lk, 1.0f, ld_v};
   const long long t4 = (long long)(lq > lk ? lq : lk) * bh * hd / 4;
   const dim3 grid((unsigned)((t4 + 255) / 256), 3);
-  if (nsplit == 1) pack_rows_multi_kernel<1><<<grid, 256, 0, s>>>(jobs, b, h, hd);
-  else if (nsplit == 2) pack_rows_multi_kernel<2><<<grid, 256, 0, s>>>(jobs, b, h, hd);
-  else pack_rows_multi_kernel<3><<<grid, 256, 0, s>>>(jobs, b, h, hd);
+#define CODA_PACK(NS)                                                                 \
+  if (is_half) pack_rows_multi_kernel<NS, true><<<grid, 256, 0, s>>>(jobs, b, h, hd); \
+  else pack_rows_multi_kernel<NS, false><<<grid, 256, 0, s>>>(jobs, b, h, hd)
+  if (nsplit == 1) { CODA_PACK(1); } else if (nsplit == 2) { CODA_PACK(2); } else { CODA_PACK(3); }
+#undef CODA_PACK
   return launch_status();
+}
+
+int coda_attention_pack(int b, int h, int lq, int lk, int hd, int nsplit, float scale, const float *q,
+                        const float *k, const float *v, void *workspace, void *stream) {
+  const long long e = (long long)h * hd;
+  return coda_attention_pack_strided(b, h, lq, lk, hd, nsplit, scale, q, k, v, e, e, e, 0, workspace, stream);
 }
 
 int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, const void *workspace,

@@ -40,6 +40,12 @@ int coda_attention_fwd(int b, int h, int lq, int lk, int hd, int nsplit, float s
  * measurement times). */
 int coda_attention_pack(int b, int h, int lq, int lk, int hd, int nsplit, float scale, const float *q,
                         const float *k, const float *v, void *workspace, void *stream);
+/* Packing from fp32 or IEEE-half sources with a row stride: q / k / v may be slices of one fused (l, b, 3*h*hd)
+ * projection (ld = 3*h*hd) and, for the fp16 CLIP tower, are read as half without an fp32 copy.
+ * ld_* in elements, multiples of 4; is_half selects the element type of all three. */
+int coda_attention_pack_strided(int b, int h, int lq, int lk, int hd, int nsplit, float scale, const void *q,
+                                const void *k, const void *v, long long ld_q, long long ld_k, long long ld_v,
+                                int is_half, void *workspace, void *stream);
 int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, const void *workspace,
                               float *out, float *lse, float dropout_p, unsigned int seed,
                               const unsigned int *seed_dev, void *stream);

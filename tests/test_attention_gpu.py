@@ -92,3 +92,23 @@ def test_attention_backward_vs_fp64(lq, lk, b, h, hd, p):
     for name, got, exp in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
         err = ((got.double() - exp).abs().max() / exp.abs().max()).item()
         assert err < 2e-4, f"{name}: rel err {err:.2e}"
+
+
+def test_attention_forward_reads_fp16_slices_of_a_fused_projection_in_place():
+    """CLIP tower call pattern: q, k, v are fp16 column slices of one (L, B, 3E) tensor; the pack kernel reads them
+    strided and as half.  Must equal the kernel run on contiguous fp32 copies of the same values bit for bit."""
+    torch.manual_seed(3)
+    l, b, h = 50, 7, 12
+    e = h * 64
+    qkv = (torch.randn(l, b, 3 * e, device="cuda") * 0.7).half()
+    q, k, v = qkv.split(e, dim=-1)
+    assert not q.is_contiguous()
+    out_h, lse_h = attention_launch.forward(q, k, v, h, nsplit=2)
+    out_f, lse_f = attention_launch.forward(q.float().contiguous(), k.float().contiguous(), v.float().contiguous(), h, nsplit=2)
+    assert out_h.dtype == torch.float32 and torch.equal(out_h, out_f) and torch.equal(lse_h, lse_f)
+    # and an fp32 strided slice (encoder-style fused projection)
+    qkv32 = torch.randn(130, 2, 3 * 256, device="cuda")
+    q2, k2, v2 = qkv32.split(256, dim=-1)
+    o_s, _ = attention_launch.forward(q2, k2, v2, 4)
+    o_c, _ = attention_launch.forward(q2.contiguous(), k2.contiguous(), v2.contiguous(), 4)
+    assert torch.equal(o_s, o_c)
