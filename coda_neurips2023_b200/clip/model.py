@@ -24,19 +24,20 @@ from torch import nn
 from .. import ops
 
 
-def _linear(x, w, b, quick_gelu=False):
+def _linear(x, w, b, quick_gelu=False, residual=None):
     """fp16 activations x fp16 weights on the fp16 tcgen05 path (fp16 written by the epilogue,
-    QuickGELU fused); fp32 (CPU checks, small test models) through torch."""
+    QuickGELU and the block's residual connection fused); fp32 (CPU checks, small test models) through torch."""
     if x.is_cuda and x.dtype == torch.float16 and x.shape[-1] % 64 == 0:
-        return ops.linear(x, w, b, quick_gelu=quick_gelu)
+        return ops.linear(x, w, b, quick_gelu=quick_gelu, residual=residual)
     y = F.linear(x, w, b)
-    return y * torch.sigmoid(1.702 * y) if quick_gelu else y
+    y = y * torch.sigmoid(1.702 * y) if quick_gelu else y
+    return y if residual is None else residual + y
 
 
 class _MLP(nn.Sequential):
-    def forward(self, x):
+    def forward(self, x, residual=None):
         h = _linear(x, self.c_fc.weight, self.c_fc.bias, quick_gelu=True)
-        return _linear(h, self.c_proj.weight, self.c_proj.bias)
+        return _linear(h, self.c_proj.weight, self.c_proj.bias, residual=residual)
 
 
 class LayerNorm(nn.LayerNorm):
@@ -65,7 +66,7 @@ class _PackedSelfAttention(nn.Module):
         self.in_proj_bias = nn.Parameter(torch.zeros(3 * d_model))
         self.out_proj = nn.Linear(d_model, d_model)
 
-    def forward(self, x: torch.Tensor, causal: bool = False):
+    def forward(self, x: torch.Tensor, causal: bool = False, residual=None):
         q, k, v = _linear(x, self.in_proj_weight, self.in_proj_bias).split(self.embed_dim, dim=-1)
         if x.is_cuda and x.dtype == torch.float16 and not causal and self.embed_dim // self.num_heads == 64:
             # image tower: fused tcgen05 attention on 2 bf16 planes (16 mantissa bits >= fp16's 11)
@@ -74,7 +75,7 @@ class _PackedSelfAttention(nn.Module):
             out = attention_launch.forward(q, k, v, self.num_heads, nsplit=2)[0].to(x.dtype)
         else:
             out = ops.attention(q, k, v, self.num_heads, 0.0, False, causal=causal)
-        return _linear(out, self.out_proj.weight, self.out_proj.bias)
+        return _linear(out, self.out_proj.weight, self.out_proj.bias, residual=residual)
 
 
 class ResidualAttentionBlock(nn.Module):
@@ -91,8 +92,8 @@ class ResidualAttentionBlock(nn.Module):
         self.causal = causal
 
     def forward(self, x: torch.Tensor):  # (L, N, D)
-        x = x + self.attn(self.ln_1(x), causal=self.causal)
-        return x + self.mlp(self.ln_2(x))
+        x = self.attn(self.ln_1(x), causal=self.causal, residual=x)      # x + attn(ln_1(x))
+        return self.mlp(self.ln_2(x), residual=x)                         # x + mlp(ln_2(x))
 
 
 class Transformer(nn.Module):

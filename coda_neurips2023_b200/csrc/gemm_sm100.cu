@@ -123,7 +123,7 @@ template <int NSPLIT, int BN, int STAGES, bool FP16, bool MN>
 __global__ void __launch_bounds__(256, 1)
 gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, int b_batched, int ksplit, int batch_n,
                const float *__restrict__ bias_in, int act, int out_half, void *__restrict__ c_void, long long ldc,
-               long long c_batch_stride, int tma_store) {
+               long long c_batch_stride, int tma_store, const void *__restrict__ residual, long long ldr) {
   // PERSISTENT: each CTA walks work items w = blockIdx.x, blockIdx.x + gridDim.x, ...;  a work item is
   // (m-tile, n-tile, batch, k-split).  The accumulator is double-buffered in TMEM (2 x BN columns) so
   // the epilogue warps drain tile i while the MMA warp already accumulates tile i+1.
@@ -313,6 +313,27 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
 #pragma unroll
             for (int t = 0; t < CHUNK; ++t) v[t] = __fdividef(v[t], 1.0f + __expf(-1.702f * v[t]));
           }
+          if (FP16 && residual != nullptr && row < m) {
+            // fused residual connection (CLIP blocks: x + proj(...)): this thread's row, one full 128-byte line
+            const __half *rr = reinterpret_cast<const __half *>(residual) + (size_t)row * ldr + col0;
+            if (col0 + CHUNK <= n) {
+#pragma unroll
+              for (int t = 0; t < CHUNK; t += 8) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(rr + t));
+                const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float2 f = __half22float2(h2[u]);
+                  v[t + 2 * u] += f.x;
+                  v[t + 2 * u + 1] += f.y;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < CHUNK; ++t)
+                if (col0 + t < n) v[t] += __half2float(rr[t]);
+            }
+          }
           // the previous chunk's store must have read the staging tile before it is rewritten
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
@@ -445,7 +466,8 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
 
 template <int NSPLIT, int BN, int STAGES, bool FP16, bool MN = false>
 int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_batched, const float *bias, int relu,
-                void *c_out, long long ldc, long long c_batch_stride, cudaStream_t s, int out_half = 0) {
+                void *c_out, long long ldc, long long c_batch_stride, cudaStream_t s, int out_half = 0,
+                const void *residual = nullptr, long long ldr = 0) {
   float *c = reinterpret_cast<float *>(c_out);
   // split-K when the output has few tiles but the contraction is long (weight gradients)
   const long long tiles = (long long)((m + BM - 1) / BM) * ((n + BN - 1) / BN) * batch;
@@ -491,8 +513,10 @@ int launch_gemm(const GemmMaps &maps, int batch, int m, int n, int kpad, int b_b
     if (num_sms <= 0) num_sms = 148;
   }
   const unsigned grid = (unsigned)(nwork < num_sms ? nwork : num_sms);
+  if (residual && (tma_store != 1 || !FP16 || batch != 1 || (ldr & 7) != 0 || ((uintptr_t)residual & 15) != 0))
+    return CODA_EINVAL;   // the fused residual exists on the fp16 TMA-store epilogue only
   kern<<<grid, 256, smem, s>>>(lmaps, m, n, kpad, b_batched, ksplit, batch, bias, relu, out_half, c_out, ldc,
-                               c_batch_stride, tma_store);
+                               c_batch_stride, tma_store, residual, ldr);
   return launch_status();
 }
 
@@ -551,6 +575,14 @@ int coda_gemm_nt_ex(int nsplit, int is_fp16, int batch, int m, int n, int kpad, 
                     long long a_plane_stride, long long a_batch_stride, const void *b, long long b_plane_stride,
                     long long b_batch_stride, const float *bias, int relu, int out_half, void *c, long long ldc,
                     long long c_batch_stride, void *stream) {
+  return coda_gemm_nt_res(nsplit, is_fp16, batch, m, n, kpad, a, a_plane_stride, a_batch_stride, b, b_plane_stride,
+                          b_batch_stride, bias, relu, out_half, nullptr, 0, c, ldc, c_batch_stride, stream);
+}
+
+int coda_gemm_nt_res(int nsplit, int is_fp16, int batch, int m, int n, int kpad, const void *a,
+                     long long a_plane_stride, long long a_batch_stride, const void *b, long long b_plane_stride,
+                     long long b_batch_stride, const float *bias, int relu, int out_half, const void *residual,
+                     long long ldr, void *c, long long ldc, long long c_batch_stride, void *stream) {
   if (nsplit < 1 || nsplit > 3 || batch < 0 || m < 0 || n < 0 || kpad < 0 || kpad % 64 != 0) return CODA_EINVAL;
   if (is_fp16 && nsplit != 1) return CODA_EINVAL;
   if (batch == 0 || m == 0 || n == 0) return CODA_OK;
@@ -569,7 +601,8 @@ int coda_gemm_nt_ex(int nsplit, int is_fp16, int batch, int m, int n, int kpad, 
   cudaStream_t s = (cudaStream_t)stream;
   const int bb = b_batch_stride ? 1 : 0;
 #define CODA_GEMM(NS, BN_, ST, F16) \
-  return launch_gemm<NS, BN_, ST, F16>(maps, batch, m, n, kpad, bb, bias, relu, c, ldc, c_batch_stride, s, out_half)
+  return launch_gemm<NS, BN_, ST, F16>(maps, batch, m, n, kpad, bb, bias, relu, c, ldc, c_batch_stride, s, out_half, \
+                                       residual, ldr)
   if (is_fp16) {
     if (bn == 64) CODA_GEMM(1, 64, 6, true);
     CODA_GEMM(1, 128, 6, true);

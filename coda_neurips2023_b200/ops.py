@@ -242,7 +242,8 @@ def pack_split(x: torch.Tensor, rows: int, k: int, row_stride: int, k_stride: in
 
 
 def gemm_nt(a_planes: torch.Tensor, b_planes: torch.Tensor, m: int, n: int, bias=None, relu: bool = False,
-            out: torch.Tensor | None = None, act: int | None = None, out_dtype=torch.float32) -> torch.Tensor:
+            out: torch.Tensor | None = None, act: int | None = None, out_dtype=torch.float32,
+            residual: torch.Tensor | None = None) -> torch.Tensor:
     """C[b] = A[b] @ B[b]^T (+ bias) from packed planes (nsplit, batch, rows, kpad); B may have batch 1
     (shared weights).  fp16 planes (nsplit == 1) select the fp16 tensor-core path.  Returns fp32 (batch, m, n)."""
     _need_cuda(a_planes, "gemm_nt")
@@ -255,11 +256,14 @@ def gemm_nt(a_planes: torch.Tensor, b_planes: torch.Tensor, m: int, n: int, bias
         out = torch.empty((batch, m, n), dtype=out_dtype, device=a_planes.device)
     if act is None:
         act = 1 if relu else 0
+    if residual is not None:
+        assert residual.dtype == torch.float16 and residual.shape == (m, n) and residual.stride(1) == 1
     with torch.cuda.device(a_planes.device):
-        st = lib().coda_gemm_nt_ex(
+        st = lib().coda_gemm_nt_res(
             _i(nsplit), _i(1 if is_fp16 else 0), _i(batch), _i(m), _i(n), _i(kpad), ptr(a_planes),
             _ll(a_planes.stride(0)), _ll(a_planes.stride(1)), ptr(b_planes), _ll(b_planes.stride(0)),
             _ll(b_planes.stride(1) if bb > 1 else 0), ptr(bias), _i(act), _i(1 if out.dtype == torch.float16 else 0),
+            ptr(residual), _ll(residual.stride(0) if residual is not None else 0),
             ptr(out), _ll(out.stride(1)), _ll(out.stride(0)), stream_of(a_planes))
     check(st, "gemm_nt")
     return out
@@ -409,7 +413,7 @@ def _bias_fp32(bias):
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool = False, nsplit: int | None = None,
-           quick_gelu: bool = False):
+           quick_gelu: bool = False, residual: torch.Tensor | None = None):
     """y = x @ weight^T + bias over the last dim of x, on the tcgen05 GEMM (fp32 in / out, bf16
     split-operand accumulation); fp16 x / weight take the fp16 tensor-core path (inference only)."""
     _need_cuda(x, "linear")
@@ -420,10 +424,18 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool = False,
     if x2.dtype == torch.float16:
         assert weight.dtype == torch.float16 and k % 64 == 0, "fp16 path needs fp16 weights and K % 64 == 0"
         x2 = x2.contiguous()
+        res2 = None
+        if residual is not None:      # y = act(x W^T + b) + residual, added in the GEMM epilogue
+            res2 = residual.reshape(-1, n)
+            if res2.dtype != torch.float16 or res2.stride(1) != 1 or res2.stride(0) % 8 != 0 or n % 8 != 0:
+                res2 = None
         y = gemm_nt(x2.view(1, 1, x2.shape[0], k), weight.detach().contiguous().view(1, 1, n, k), x2.shape[0], n,
                     bias=None if bias is None else _bias_fp32(bias), act=2 if quick_gelu else (1 if relu else 0),
-                    out_dtype=torch.float16)[0]
-        return y.reshape(*lead, n)
+                    out_dtype=torch.float16, residual=res2)[0]
+        y = y.reshape(*lead, n)
+        return y + residual if (residual is not None and res2 is None) else y
+    if residual is not None:
+        raise NotImplementedError("fused residual exists on the fp16 inference path only")
     if x2.stride(-1) != 1:
         x2 = x2.contiguous()
     w2 = weight.reshape(n, -1)

@@ -55,6 +55,15 @@ int coda_gemm_nt_ex(int nsplit, int is_fp16, int batch, int m, int n, int kpad, 
                     long long b_plane_stride, long long b_batch_stride, const float *bias, int act,
                     int out_half, void *c, long long ldc, long long c_batch_stride, void *stream);
 
+/* As coda_gemm_nt_ex, plus a fused residual connection on the fp16 path: C = act(A B^T + bias) + residual,
+ * residual (m, n) IEEE half with row stride ldr (multiple of 8), batch == 1, fp16 operands and output
+ * (the `x + proj(...)` of the CLIP residual blocks, CLIP/clip/model.py:283-288).  NULL = no residual. */
+int coda_gemm_nt_res(int nsplit, int is_fp16, int batch, int m, int n, int kpad, const void *a,
+                     long long a_plane_stride, long long a_batch_stride, const void *b,
+                     long long b_plane_stride, long long b_batch_stride, const float *bias, int act,
+                     int out_half, const void *residual, long long ldr, void *c, long long ldc,
+                     long long c_batch_stride, void *stream);
+
 /*
  * "TN" form for weight gradients: C[m][n] = sum_{r < mc} A[r][m] * B[r][n], with A planes
  * [nsplit][mc][lda] and B planes [nsplit][mc][ldb] (row-major, lda / ldb multiples of 64), i.e. the

@@ -129,3 +129,24 @@ def test_gemm_fp16_output_and_quick_gelu():
     y2 = ops.linear(x, w, None)
     ref2 = torch.nn.functional.linear(x.double(), w.double())
     assert ((y2.double() - ref2).abs().max() / ref2.abs().max()).item() < 2e-3
+
+
+def test_fp16_linear_with_fused_residual_and_gelu():
+    """CLIP block pattern: y = x_res + (QuickGELU?)(x W^T + b), residual added in the GEMM epilogue."""
+    torch.manual_seed(5)
+    m, k, n = 300, 768, 768          # ragged last row tile
+    x = (torch.randn(m, k, device="cuda") * 0.2).half()
+    w = (torch.randn(n, k, device="cuda") * 0.05).half()
+    b = (torch.randn(n, device="cuda") * 0.1).half()
+    res = torch.randn(m, n, device="cuda").half()
+    for gelu in (False, True):
+        y = ops.linear(x, w, b, quick_gelu=gelu, residual=res)
+        lin = x.double() @ w.double().t() + b.double()
+        if gelu:
+            lin = lin * torch.sigmoid(1.702 * lin)
+        ref = lin + res.double()
+        assert y.dtype == torch.float16 and y.shape == (m, n)
+        assert ((y.double() - ref).abs().max() / ref.abs().max()).item() < 2e-3     # fp16 output rounding
+    # 3-D input / residual (L, N, D) as the tower passes them
+    x3, r3 = x.view(50, 6, k), res.view(50, 6, n)
+    assert torch.equal(ops.linear(x3, w, b, residual=r3).view(m, n), ops.linear(x, w, b, residual=res))
