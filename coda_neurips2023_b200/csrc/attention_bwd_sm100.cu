@@ -321,6 +321,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B,
   __shared__ __align__(8) uint64_t kv_full, q_full[C::QST], q_empty[C::QST], s_full, p_full, p_empty, acc_done;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_lse[2][64], s_delta[2][64];
+  __shared__ uint32_t s_seed[2][2][64];   // dropout stream seeds of (64 queries) x (this CTA's two key tiles)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128, bh = blockIdx.y;
   const int ntiles = (Lq + 63) / 64;
@@ -428,6 +429,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B,
         const int t = row & 63, qi = i * 64 + t;
         if (row < 64) s_lse[i & 1][t] = qi < Lq ? __ldg(lse + (size_t)bh * Lq + qi) * LOG2E : 0.f;
         else s_delta[i & 1][t] = qi < Lq ? __ldg(delta + (size_t)bh * Lq + qi) : 0.f;
+        // one strong hash per (query, key tile), computed once and shared by the 64 key rows of that tile
+        if (dropout) s_seed[i & 1][row >> 6][t] = drop_tile_seed(seed, (uint32_t)bh, (uint32_t)qi, (uint32_t)(krow >> 6));
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&s_full, (uint32_t)i & 1u);
@@ -450,10 +453,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B,
           const float p = (c < qvalid && valid_row) ? ex2_approx_b(fmaf(s, LOG2E, -s_lse[i & 1][c])) : 0.f;
           const float dp = __uint_as_float(pr[c >> 5][c & 31]);
           float m = 1.0f;
-          if (dropout) {
-            const uint32_t ts = drop_tile_seed(seed, (uint32_t)bh, (uint32_t)(i * 64 + c), (uint32_t)(krow >> 6));
-            m = (ts * ja + jc >= thresh32) ? keep_scale : 0.f;
-          }
+          if (dropout) m = (s_seed[i & 1][row >> 6][c] * ja + jc >= thresh32) ? keep_scale : 0.f;
           pt[e] = p * m;
           ds[e] = p * (dp * m - s_delta[i & 1][c]);
         }
