@@ -112,13 +112,7 @@ attn_bwd_dq_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B, 
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, bh = blockIdx.y;
-  // gridDim.z > 1: the key range is split across CTAs (few query tiles, long key sequences -- the decoder's
-  // cross attention would otherwise occupy 64 of 148 SMs); each CTA owns tiles [jt0, jt0 + ntiles) and adds its
-  // partial dQ into the zero-initialised output.
-  const int ntiles_all = (Lk + 63) / 64;
-  const int per_split = (ntiles_all + (int)gridDim.z - 1) / (int)gridDim.z;
-  const int jt0 = (int)blockIdx.z * per_split;
-  const int ntiles = min(per_split, ntiles_all - jt0);   // >= 1 by construction of gridDim.z (host)
+  const int ntiles = (Lk + 63) / 64;
 
   if (warp == 1 && lane == 0) {
     mbar_init(&q_full, 1);
@@ -156,7 +150,7 @@ attn_bwd_dq_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B, 
         for (int p = 0; p < NS; ++p)
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb)
-            tma_load_3d(smem + C::K_OFF + (ks * NS + p) * C::KP + kb * C::T64, &maps.k[p], &k_full[ks], kb * 64, (jt0 + j) * 64, bh);
+            tma_load_3d(smem + C::K_OFF + (ks * NS + p) * C::KP + kb * C::T64, &maps.k[p], &k_full[ks], kb * 64, j * 64, bh);
       }
       __syncwarp();
       mbar_wait(&v_empty[vs], ((uint32_t)(j / C::VST) & 1u) ^ 1u);
@@ -166,7 +160,7 @@ attn_bwd_dq_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B, 
         for (int p = 0; p < NS; ++p)
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb)
-            tma_load_3d(smem + C::V_OFF + (vs * NS + p) * C::KP + kb * C::T64, &maps.v[p], &v_full[vs], kb * 64, (jt0 + j) * 64, bh);
+            tma_load_3d(smem + C::V_OFF + (vs * NS + p) * C::KP + kb * C::T64, &maps.v[p], &v_full[vs], kb * 64, j * 64, bh);
       }
       __syncwarp();
     }
@@ -247,9 +241,9 @@ attn_bwd_dq_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B, 
       tmem_ld_wait();
       // the previous tile's dS must have been consumed by its MMAs before it is overwritten
       if (j > 0) { mbar_wait(&ds_empty, ((uint32_t)j & 1u) ^ 1u); tc_fence_after(); }
-      const int kvalid = Lk - (jt0 + j) * 64;
+      const int kvalid = Lk - j * 64;
       uint32_t ts = 0;
-      if (dropout) ts = drop_tile_seed(seed, (uint32_t)bh, (uint32_t)qrow, (uint32_t)(jt0 + j));
+      if (dropout) ts = drop_tile_seed(seed, (uint32_t)bh, (uint32_t)qrow, (uint32_t)j);
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         float ds[16];
@@ -278,15 +272,12 @@ attn_bwd_dq_kernel(const __grid_constant__ BwdMaps maps, int Lq, int Lk, int B, 
         uint32_t r[32];
         tmem_ld_32x32(tm + lane_base + (uint32_t)(C::DQ_COL + c0), r);   // warp-collective: every lane executes it
         tmem_ld_wait();
-        if (valid_row && gridDim.z == 1) {
+        if (valid_row) {
 #pragma unroll
           for (int t = 0; t < 32; t += 4)
             *reinterpret_cast<float4 *>(orow + c0 + t) =
                 make_float4(__uint_as_float(r[t]) * scale, __uint_as_float(r[t + 1]) * scale,
                             __uint_as_float(r[t + 2]) * scale, __uint_as_float(r[t + 3]) * scale);
-        } else if (valid_row) {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) atomicAdd(orow + c0 + t, __uint_as_float(r[t]) * scale);
         }
       }
     }
@@ -515,21 +506,7 @@ int launch_bwd(const BwdMaps &mq, const BwdMaps &mk, int b, int h, int lq, int l
     configured = true;
   }
   const int bh = b * h;
-  // few query tiles and many key tiles (decoder cross attention): split the key range so the GPU is filled
-  const int qtiles = (lq + 127) / 128, ktiles = (lk + 63) / 64;
-  int splits = 1;
-  if ((long long)qtiles * bh < 148 && ktiles >= 8) {
-    splits = (int)(296 / ((long long)qtiles * bh));
-    if (splits > ktiles / 4) splits = ktiles / 4;
-    if (splits < 1) splits = 1;
-    const int per = (ktiles + splits - 1) / splits;
-    splits = (ktiles + per - 1) / per;          // every split owns at least one tile
-  }
-  if (splits > 1) {
-    cudaError_t e = cudaMemsetAsync(dq, 0, (size_t)lq * b * h * HD * sizeof(float), s);
-    if (e != cudaSuccess) return (int)e;
-  }
-  attn_bwd_dq_kernel<HD><<<dim3(qtiles, bh, splits), 256, DqCfg<HD>::TOTAL + 1024, s>>>(
+  attn_bwd_dq_kernel<HD><<<dim3((lq + 127) / 128, bh), 256, DqCfg<HD>::TOTAL + 1024, s>>>(
       mq, lq, lk, b, h, scale, lse, delta, dq, dropout_p, seed, seed_dev);
   attn_bwd_dkv_kernel<HD><<<dim3((lk + 127) / 128, bh), 256, DkvCfg<HD>::TOTAL + 1024, s>>>(
       mk, lq, lk, b, h, lse, delta, dk, dv, dropout_p, seed, seed_dev);
