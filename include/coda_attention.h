@@ -1,5 +1,5 @@
 /*
- * coda_attention.h -- C-ABI of the fused tcgen05 multi-head attention (forward).
+ * coda_attention.h -- C-ABI of the fused tcgen05 multi-head attention (forward and backward).
  *
  * Replaces the attention core of torch.nn.MultiheadAttention as the reference calls it
  * in TransformerEncoderLayer / TransformerDecoderLayer (models/transformer.py:461-479,
@@ -13,12 +13,14 @@
  * reference's modules use);  out (lq, b, h*hd) fp32;  lse (b*h, lq) fp32 log-sum-exp of
  * the scaled scores (for the backward pass), may be NULL.
  * hd in {64, 128}.  nsplit in {1, 2, 3}: bf16 planes per fp32 operand (see coda_gemm.h).
- * dropout_p in [0, 1): element (bh, i, j) of the probabilities is kept iff
- *   (mix32(seed + bh*0x9E3779B1 + i*0x85EBCA77 + j*0xC2B2AE3D) & 0xFFFFFF) >= floor(p * 2^24)
- * with mix32(h): h ^= h>>15; h *= 0x2C1B3C6D; h ^= h>>12; h *= 0x297A2D39; h ^= h>>15
- * (32-bit wrap-around; the effective seed is `seed` + *seed_dev when seed_dev, a device
- * counter, is given), and scaled by 1/(1-p) -- a counter-based mask, so the backward
- * can regenerate it without storing it.
+ * dropout_p in [0, 1): a counter-based mask, so the backward regenerates it without storing it.  One strong
+ * hash per (row i, 64-key tile t) seeds a 32-bit LCG that is stepped along the keys of the tile:
+ *   s   = mix32(seed + bh*0x9E3779B1 + i*0x85EBCA77 + t*0xC2B2AE3D)      t = j / 64
+ *   x_c = A^(c+1) s + C (A^c + ... + 1)  (mod 2^32),  c = j % 64,  A = 747796405, C = 2891336453
+ *   element (bh, i, j) is kept iff x_c >= floor(p * 2^32);  kept probabilities are scaled by 1/(1-p)
+ * with mix32(h): h ^= h>>15; h *= 0x2C1B3C6D; h ^= h>>12; h *= 0x297A2D39; h ^= h>>15 (32-bit wrap-around);
+ * the effective seed is `seed` + *seed_dev when seed_dev, a device counter, is given.
+ * (coda_neurips2023_b200/attention_launch.py:dropout_keep restates the formula for the tests.)
  * workspace: coda_attention_workspace_bytes(...) bytes of device scratch (packed operand planes).
  */
 #ifndef CODA_ATTENTION_H
