@@ -20,3 +20,24 @@ def test_model_and_criterion_match_reference_on_cpu(name):
         errs = mpc.compare(model, out, loss, loss_dict, golden, rtol=2e-4, atol=1e-5)
     worst = max(errs, key=errs.get)
     print(f"{name}: worst {worst} = {errs[worst]:.2e}")
+
+
+@pytest.mark.parametrize("name", list(mpc.CASES))
+def test_stacked_criterion_call_equals_the_per_layer_loop(name):
+    """SetCriterion.forward takes the seven auxiliary decoder outputs in ONE stacked call when the model hands it
+    `stacked_layers`; without that key (a reference-style outputs dict) it loops layer by layer like
+    criterion.py:1205-1216.  Both must give the same total and the same loss_dict entries."""
+    torch.manual_seed(0)
+    with cpu_shims.installed():
+        args, model, criterion, inputs, _ = mpc.build(name, "cpu")
+        np.random.seed(123)
+        out = model(inputs, curr_epoch=0)
+        assert "stacked_layers" in out and len(out["aux_outputs"]) >= 1
+        loss_a, dict_a = criterion(out, dict(inputs))
+        plain = {"outputs": dict(out["outputs"]), "aux_outputs": [dict(a) for a in out["aux_outputs"]]}
+        loss_b, dict_b = criterion(plain, dict(inputs))
+    assert set(dict_a) == set(dict_b)
+    assert abs(float(loss_a) - float(loss_b)) <= 2e-6 * abs(float(loss_b))
+    for k in dict_a:
+        a, b = float(dict_a[k]), float(dict_b[k])
+        assert abs(a - b) <= 2e-6 * max(abs(b), 1e-3), k
