@@ -40,7 +40,7 @@ def _row_strided(t: torch.Tensor):
     return None
 
 
-def forward(q, k, v, nhead: int, dropout_p: float = 0.0, salt: int = 0, nsplit: int = 3):
+def forward(q, k, v, nhead: int, dropout_p: float = 0.0, salt: int = 0, nsplit: int = 3, half_out: bool = False):
     """q (Lq, B, E), k / v (Lk, B, E), fp32 or fp16 (all three alike), each either contiguous or a row-strided
     slice of a fused projection -> (out (Lq, B, E) fp32, lse (B*H, Lq))."""
     lq, b, e = q.shape
@@ -53,7 +53,8 @@ def forward(q, k, v, nhead: int, dropout_p: float = 0.0, salt: int = 0, nsplit: 
     if any(ld is None for ld in lds):
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         lds = [e, e, e]
-    out = torch.empty((lq, b, e), dtype=torch.float32, device=q.device)
+    half_out = bool(half_out) and lk <= 64 and hd == 64 and nsplit <= 2   # the single-tile instance only
+    out = torch.empty((lq, b, e), dtype=torch.float16 if half_out else torch.float32, device=q.device)
     lse = torch.empty((b * nhead, lq), dtype=torch.float32, device=q.device)
     L = lib()
     L.coda_attention_workspace_bytes.restype = ctypes.c_longlong
@@ -66,9 +67,9 @@ def forward(q, k, v, nhead: int, dropout_p: float = 0.0, salt: int = 0, nsplit: 
                                            ctypes.c_float(float(hd) ** -0.5), ptr(q), ptr(k), ptr(v), cl(lds[0]),
                                            cl(lds[1]), cl(lds[2]), ci(1 if is_half else 0), ptr(ws), stream_of(q))
         check(st, "attention_pack")
-        st = L.coda_attention_fwd_packed(ci(b), ci(nhead), ci(lq), ci(lk), ci(hd), ci(nsplit), ptr(ws), ptr(out),
-                                         ptr(lse), ctypes.c_float(dropout_p), ctypes.c_uint(salt & 0xFFFFFFFF),
-                                         ptr(seed_dev), stream_of(q))
+        st = L.coda_attention_fwd_packed_ex(ci(b), ci(nhead), ci(lq), ci(lk), ci(hd), ci(nsplit), ptr(ws), ptr(out),
+                                            ci(1 if half_out else 0), ptr(lse), ctypes.c_float(dropout_p),
+                                            ctypes.c_uint(salt & 0xFFFFFFFF), ptr(seed_dev), stream_of(q))
     check(st, "attention_fwd")
     return out, lse
 

@@ -72,7 +72,7 @@ class _PackedSelfAttention(nn.Module):
             # image tower: fused tcgen05 attention on 2 bf16 planes (16 mantissa bits >= fp16's 11)
             from .. import attention_launch
             # q / k / v stay fp16 slices of the fused projection: the pack kernel reads them in place
-            out = attention_launch.forward(q, k, v, self.num_heads, nsplit=2)[0].to(x.dtype)
+            out = attention_launch.forward(q, k, v, self.num_heads, nsplit=2, half_out=True)[0].to(x.dtype)
         else:
             out = ops.attention(q, k, v, self.num_heads, 0.0, False, causal=causal)
         return _linear(out, self.out_proj.weight, self.out_proj.bias, residual=residual)

@@ -107,7 +107,7 @@ template <int HD, int NSPLIT, bool ONE_TILE>
 __global__ void __launch_bounds__(AttnCfg<HD, NSPLIT, ONE_TILE>::THREADS, AttnCfg<HD, NSPLIT, ONE_TILE>::MIN_CTAS)
 attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__restrict__ qplanes, int Lq, int Lk,
                 int B, int H, float *__restrict__ out, float *__restrict__ lse, float drop_p, uint32_t seed,
-                const uint32_t *__restrict__ seed_dev) {
+                const uint32_t *__restrict__ seed_dev, int out_half) {
   using SM = AttnCfg<HD, NSPLIT, ONE_TILE>;
   if (seed_dev) seed += __ldg(seed_dev);  // per-step counter kept on the device (CUDA-graph friendly)
   constexpr int KB = SM::KB, NWG = SM::NWG, NP = SM::NP, NST = SM::NST;
@@ -345,18 +345,32 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
         const int qrow = q0 + row;
         const float inv = keep_scale / l_run;
         const int b = bh / H, h = bh - b * H;
-        float *orow = out + ((size_t)qrow * B + b) * (size_t)(H * HD) + (size_t)h * HD;
+        const size_t ooff = ((size_t)qrow * B + b) * (size_t)(H * HD) + (size_t)h * HD;
+        float *orow = out + ooff;
+        __half *hrow = reinterpret_cast<__half *>(out) + ooff;    // out_half: the fp16 tower takes its dtype back directly
 #pragma unroll
         for (int c0 = 0; c0 < HD; c0 += 32) {
           uint32_t orr[32];
           tmem_ld_32x32(my_o + c0, orr);
           tmem_ld_wait();
           if (qrow < Lq) {
+            if (out_half) {
 #pragma unroll
-            for (int t = 0; t < 32; t += 4)
-              *reinterpret_cast<float4 *>(orow + c0 + t) =
-                  make_float4(__uint_as_float(orr[t]) * inv, __uint_as_float(orr[t + 1]) * inv,
-                              __uint_as_float(orr[t + 2]) * inv, __uint_as_float(orr[t + 3]) * inv);
+              for (int t = 0; t < 32; t += 4) {
+                const __half2 lo = __floats2half2_rn(__uint_as_float(orr[t]) * inv, __uint_as_float(orr[t + 1]) * inv);
+                const __half2 hi = __floats2half2_rn(__uint_as_float(orr[t + 2]) * inv, __uint_as_float(orr[t + 3]) * inv);
+                uint2 w;
+                w.x = *reinterpret_cast<const uint32_t *>(&lo);
+                w.y = *reinterpret_cast<const uint32_t *>(&hi);
+                *reinterpret_cast<uint2 *>(hrow + c0 + t) = w;
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 32; t += 4)
+                *reinterpret_cast<float4 *>(orow + c0 + t) =
+                    make_float4(__uint_as_float(orr[t]) * inv, __uint_as_float(orr[t + 1]) * inv,
+                                __uint_as_float(orr[t + 2]) * inv, __uint_as_float(orr[t + 3]) * inv);
+            }
           }
         }
         if (lse && qrow < Lq) lse[(size_t)bh * Lq + qrow] = m_run * LN2 + logf(l_run);
@@ -413,7 +427,8 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
 
 template <int HD, int NSPLIT, bool ONE_TILE = false>
 int launch_attn(const AttnMaps &maps, const __nv_bfloat16 *qplanes, int Lq, int Lk, int B, int H, float *out,
-                float *lse, float drop_p, uint32_t seed, const uint32_t *seed_dev, cudaStream_t s) {
+                float *lse, float drop_p, uint32_t seed, const uint32_t *seed_dev, cudaStream_t s, int out_half = 0) {
+  if (out_half && !ONE_TILE) return CODA_EINVAL;   // fp16 output exists on the single-tile (CLIP tower) instance
   using SM = AttnCfg<HD, NSPLIT, ONE_TILE>;
   constexpr size_t smem = SM::TOTAL + 1024;
   auto kern = attn_fwd_kernel<HD, NSPLIT, ONE_TILE>;
@@ -424,7 +439,7 @@ int launch_attn(const AttnMaps &maps, const __nv_bfloat16 *qplanes, int Lq, int 
     configured = true;
   }
   const dim3 grid((Lq + QT - 1) / QT, B * H);
-  kern<<<grid, SM::THREADS, smem, s>>>(maps, qplanes, Lq, Lk, B, H, out, lse, drop_p, seed, seed_dev);
+  kern<<<grid, SM::THREADS, smem, s>>>(maps, qplanes, Lq, Lk, B, H, out, lse, drop_p, seed, seed_dev, out_half);
   return launch_status();
 }
 
@@ -481,6 +496,14 @@ int coda_attention_pack(int b, int h, int lq, int lk, int hd, int nsplit, float 
 int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, const void *workspace,
                               float *out, float *lse, float dropout_p, unsigned int seed,
                               const unsigned int *seed_dev, void *stream) {
+  return coda_attention_fwd_packed_ex(b, h, lq, lk, hd, nsplit, workspace, out, 0, lse, dropout_p, seed, seed_dev,
+                                      stream);
+}
+
+int coda_attention_fwd_packed_ex(int b, int h, int lq, int lk, int hd, int nsplit, const void *workspace,
+                                 void *out_v, int out_half, float *lse, float dropout_p, unsigned int seed,
+                                 const unsigned int *seed_dev, void *stream) {
+  float *out = reinterpret_cast<float *>(out_v);
   int st = attn_check(b, h, lq, lk, hd, nsplit);
   if (st != CODA_OK) return st;
   if (b == 0 || lq == 0) return CODA_OK;
@@ -499,9 +522,10 @@ int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, 
   }
 #define CODA_ATTN(HD_, NS) return launch_attn<HD_, NS>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s)
   if (hd == 64 && lk <= KT && nsplit <= 2) {   // single key tile (CLIP image tower): two CTAs per SM
-    if (nsplit == 1) return launch_attn<64, 1, true>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s);
-    return launch_attn<64, 2, true>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s);
+    if (nsplit == 1) return launch_attn<64, 1, true>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s, out_half);
+    return launch_attn<64, 2, true>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s, out_half);
   }
+  if (out_half) return CODA_EINVAL;
   if (hd == 64) {
     if (nsplit == 1) CODA_ATTN(64, 1);
     if (nsplit == 2) CODA_ATTN(64, 2);

@@ -52,6 +52,12 @@ int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, 
                               float *out, float *lse, float dropout_p, unsigned int seed,
                               const unsigned int *seed_dev, void *stream);
 
+/* As coda_attention_fwd_packed; out_half != 0 writes `out` as IEEE half (lk <= 64, hd == 64, nsplit <= 2 only:
+ * the CLIP image tower, whose activations are fp16). */
+int coda_attention_fwd_packed_ex(int b, int h, int lq, int lk, int hd, int nsplit, const void *workspace,
+                                 void *out, int out_half, float *lse, float dropout_p, unsigned int seed,
+                                 const unsigned int *seed_dev, void *stream);
+
 /*
  * Backward of coda_attention_fwd (hd 64 or 128): two fused tcgen05 kernels (dQ row-wise; dK, dV
  * column-wise) that recompute the probabilities from `lse`, regenerate the dropout mask from the same

@@ -106,6 +106,9 @@ def test_attention_forward_reads_fp16_slices_of_a_fused_projection_in_place():
     out_h, lse_h = attention_launch.forward(q, k, v, h, nsplit=2)
     out_f, lse_f = attention_launch.forward(q.float().contiguous(), k.float().contiguous(), v.float().contiguous(), h, nsplit=2)
     assert out_h.dtype == torch.float32 and torch.equal(out_h, out_f) and torch.equal(lse_h, lse_f)
+    # fp16 output straight from the kernel (single-tile instance) = the fp32 result rounded once
+    out_16, _ = attention_launch.forward(q, k, v, h, nsplit=2, half_out=True)
+    assert out_16.dtype == torch.float16 and torch.equal(out_16, out_h.half())
     # and an fp32 strided slice (encoder-style fused projection)
     qkv32 = torch.randn(130, 2, 3 * 256, device="cuda")
     q2, k2, v2 = qkv32.split(256, dim=-1)
