@@ -1,5 +1,5 @@
-"""Launcher of the tcgen05 attention forward (include/coda_attention.h) and the torch-side
-twin of its counter-based dropout mask (used by the interim autograd backward)."""
+"""Launchers of the tcgen05 attention forward and backward (include/coda_attention.h) and the
+torch-side twin of their counter-based dropout mask (used by the tests to build the same mask)."""
 from __future__ import annotations
 
 import ctypes

@@ -2,8 +2,10 @@
 
 forward : one launch per attention call; S = Q K^T, online softmax and O = P V are
           tiled through TMEM, the (Lq x Lk) probabilities never reach HBM.
-backward: (this round) re-derives P with cuBLAS batched GEMMs under autograd; the
-          tcgen05 backward kernel is the next step.
+backward: two tcgen05 kernels (dQ; dK / dV) that recompute P tile by tile from the saved
+          log-sum-exp (csrc/attention_bwd_sm100.cu); nothing of size Lq x Lk is stored.
+`_math` below is the plain-tensor formulation used by the tests as the numerics reference and by
+the causal CLIP text tower, which runs once at model construction (never inside the step).
 """
 from __future__ import annotations
 
@@ -16,8 +18,8 @@ from ._lib import check, lib, ptr, stream_of
 
 
 def _math(q, k, v, nhead, dropout_p, training, causal, keep=None):
-    """softmax(q k^T / sqrt(hd)) v per head with torch bmm (cuBLAS): numerics reference in tests and
-    the recompute of the interim backward.  `keep` is an explicit (B*H, Lq, Lk) dropout keep-mask."""
+    """softmax(q k^T / sqrt(hd)) v per head in plain tensor ops: numerics reference in tests and the
+    init-time CLIP text tower.  `keep` is an explicit (B*H, Lq, Lk) dropout keep-mask."""
     lq, b, e = q.shape
     lk = k.shape[0]
     hd = e // nhead
@@ -65,7 +67,7 @@ def attention(q, k, v, nhead, dropout_p=0.0, training=False, causal=False):
         raise RuntimeError("attention: CPU not supported")
     hd = q.shape[-1] // nhead
     if causal or q.dtype != torch.float32 or hd not in (64, 128):
-        # CLIP text tower (causal, runs once at init) and the fp16 image tower: cuBLAS path for now
+        # CLIP text tower only (causal, fp16/fp32, runs ONCE at model construction, never inside the step)
         return _math(q, k, v, nhead, dropout_p, training, causal)
     from . import attention_launch
 

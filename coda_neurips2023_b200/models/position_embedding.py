@@ -1,7 +1,7 @@
 """Coordinate positional encodings (mirror of reference models/position_embedding.py).
 
-The Fourier variant -- the one 3DETR uses -- is a single fused kernel
-(ops.fourier_pos_embed); the sine variant is kept as tensor code.
+The Fourier variant -- the one 3DETR / CoDA use -- is a single fused kernel
+(ops.fourier_pos_embed).  The sine variant is dead on the path and not built.
 """
 from __future__ import annotations
 
@@ -11,7 +11,6 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..utils.pc_util import shift_scale_points
 
 
 class PositionEmbeddingCoordsSine(nn.Module):
@@ -36,31 +35,8 @@ class PositionEmbeddingCoordsSine(nn.Module):
             self.d_pos = d_pos
 
     def get_sine_embeddings(self, xyz, num_channels, input_range):
-        xyz = xyz.clone()
-        if self.normalize:
-            xyz = shift_scale_points(xyz, src_range=input_range)
-        ndim = num_channels // xyz.shape[2]
-        if ndim % 2 != 0:
-            ndim -= 1
-        rems = num_channels - (ndim * xyz.shape[2])  # remainder goes to the first dims, two at a time
-        assert ndim % 2 == 0
-        embeds, prev_dim, dim_t = [], 0, None
-        for d in range(xyz.shape[2]):
-            cdim = ndim
-            if rems > 0:
-                cdim += 2
-                rems -= 2
-            if cdim != prev_dim:
-                dim_t = torch.arange(cdim, dtype=torch.float32, device=xyz.device)
-                dim_t = self.temperature ** (2 * (dim_t // 2) / cdim)
-            raw_pos = xyz[:, :, d]
-            if self.scale:
-                raw_pos *= self.scale
-            pos = raw_pos[:, :, None] / dim_t
-            pos = torch.stack((pos[:, :, 0::2].sin(), pos[:, :, 1::2].cos()), dim=3).flatten(2)
-            embeds.append(pos)
-            prev_dim = cdim
-        return torch.cat(embeds, dim=2).permute(0, 2, 1)
+        raise NotImplementedError("pos_type='sine' is never selected on the CoDA path (every model builds "
+                                  "PositionEmbeddingCoordsSine(pos_type='fourier')); only the Fourier kernel exists")
 
     def get_fourier_embeddings(self, xyz, num_channels=None, input_range=None):
         """xyz (B, N, 3) -> (B, num_channels, N); reference position_embedding.py:89-118."""

@@ -147,7 +147,10 @@ def make_batch(batch: int, npoints: int = 20000, seed: int = 0, max_gt: int = 64
         "gt_box_seen_sem_cls_confi": present.copy(),
     })
     # image side: SUN RGB-D-like intrinsics, small tilt, augmentation bookkeeping
-    K = np.tile(np.array([[529.5, 0, 365.0], [0, 529.5, 265.0], [0, 0, 1.0]]), (batch, 1, 1))
+    # SUN RGB-D intrinsics at 730 x 531; other image shapes (ScanNet: 1296 x 968) scale the focal length with
+    # the width and keep the principal point at the same relative position
+    f = 529.5 * w / 730.0
+    K = np.tile(np.array([[f, 0, 365.0 * w / 730.0], [0, f, 265.0 * h / 531.0], [0, 0, 1.0]]), (batch, 1, 1))
     tilt = rng.uniform(-0.05, 0.05, size=batch)
     Rtilt = np.stack([np.array([[1, 0, 0], [0, np.cos(t), -np.sin(t)], [0, np.sin(t), np.cos(t)]]) for t in tilt])
     rot = rng.uniform(-np.pi / 18, np.pi / 18, size=batch)

@@ -24,18 +24,10 @@ import _reference_harness as H  # noqa: E402
 from coda_neurips2023_b200 import synthetic  # noqa: E402
 from param_fill import fill_by_name  # noqa: E402
 
-CASES = {
-    # name: (batch, npoints, args overrides)
-    "stage1_small": (2, 3000, dict(nqueries=128, preenc_npoints=256, dec_dim=128, dec_nlayers=2, dec_ffn_dim=64,
-                                   enc_dropout=0.0, dec_dropout=0.0, mlp_dropout=0.0)),
-    "stage2_weak": (2, 2500, dict(nqueries=128, preenc_npoints=256, dec_dim=128, dec_nlayers=2, dec_ffn_dim=64,
-                                  enc_dropout=0.0, dec_dropout=0.0, mlp_dropout=0.0, if_clip_weak_labels=True,
-                                  loss_feat_seen_softmax_weakly_loss_with_novel_cate_confi_weight=1.0,
-                                  confidence_type="clip-max-prob")),
-}
-TINY_CLIP = dict(embed_dim=512, image_resolution=224, vision_layers=2, vision_width=128, vision_patch_size=32,
-                 context_length=77, vocab_size=49408, transformer_width=64, transformer_heads=1,
-                 transformer_layers=1)
+import model_parity_common as mpc  # noqa: E402  (the case table is shared with the parity tests)
+
+CASES = mpc.CASES
+TINY_CLIP = mpc.TINY_CLIP
 
 # arguments the reference reads that our make_args does not carry (weight-0 / off everywhere)
 REF_EXTRA = dict(
@@ -64,7 +56,7 @@ def reference_args(overrides):
 
 
 def run_reference(name):
-    batch, npoints, over = CASES[name]
+    batch, npoints, over, extra = mpc.case(name)
     args = reference_args(over)
     m3 = H.load("models.model_3detr")
     crit_mod = H.load("criterion")
@@ -94,12 +86,17 @@ def run_reference(name):
     fill_by_name(model, seed=3)
     # re-derive the text features from the filled CLIP (they were computed in __init__)
     with torch.no_grad():
-        model.text_features_fg = model.clip_model.encode_text(model.text).to(torch.float32)
-        model.text_features_fg_norm = model.text_features_fg / model.text_features_fg.norm(dim=1, keepdim=True)
+        if "text_rows" in extra:   # seeded random unit rows stand in for the class prompts
+            model.text_features_fg_norm = torch.from_numpy(mpc.text_rows(extra["text_rows"]))
+            model.text_features_fg = model.text_features_fg_norm.clone()
+        else:
+            model.text_features_fg = model.clip_model.encode_text(model.text).to(torch.float32)
+            model.text_features_fg_norm = model.text_features_fg / model.text_features_fg.norm(dim=1, keepdim=True)
     criterion = crit_mod.build_criterion(args, cfg)
     model.train()
     model.clip_model.eval()
-    inputs = {k: torch.from_numpy(v) for k, v in synthetic.make_batch(batch, npoints, seed=5).items()}
+    inputs = {k: torch.from_numpy(v) for k, v in
+              synthetic.make_batch(batch, npoints, seed=5, image_hw=extra.get("image_hw", (531, 730))).items()}
     np.random.seed(123)  # box selection draws (model_3detr.py:991)
     out = model(inputs, curr_epoch=0)
     loss, loss_dict = criterion(out, inputs)
@@ -109,10 +106,25 @@ def run_reference(name):
 
 KEEP = ("sem_cls_logits", "center_normalized", "size_normalized", "angle_logits", "angle_residual",
         "angle_continuous", "objectness_prob", "box_corners", "box_corners_xyz")
+GRADS = ("pre_encoder.mlp_module.layer0.conv.weight", "pre_encoder.mlp_module.layer2.conv.weight",
+         "encoder.layers.0.self_attn.in_proj_weight", "encoder.layers.2.linear1.weight",
+         "encoder_to_decoder_projection.layers.0.weight", "query_projection.layers.0.weight",
+         "decoder.layers.0.self_attn.in_proj_weight", "decoder.layers.1.multihead_attn.out_proj.weight",
+         "decoder.layers.{last}.multihead_attn.in_proj_weight", "decoder.layers.{last}.linear2.weight",
+         "mlp_heads.center_head.layers.0.weight", "mlp_heads.text_correlation_head.layers.8.weight",
+         "mlp_heads.sem_cls_head.layers.8.bias", "decoder.norm.weight")
+
+
+def thin(a: np.ndarray) -> np.ndarray:
+    """Large gradients are stored as a [::4, ::4] lattice (tests/model_parity_common.py applies the same rule)."""
+    return a[::4, ::4] if (a.ndim >= 2 and a.size > 65536) else a
 
 
 def main():
+    only = sys.argv[1:]
     for name in CASES:
+        if only and name not in only:
+            continue
         args, model, out, loss, loss_dict = run_reference(name)
         last = out["outputs"]
         blob = {f"last.{k}": last[k].detach().numpy() for k in KEEP}
@@ -122,20 +134,25 @@ def main():
         blob["last.weak_box_cate_label"] = last["weak_box_cate_label"].numpy()
         blob["last.weak_confidence_weight"] = last["weak_confidence_weight"].numpy()
         blob["text_features_fg_norm"] = model.text_features_fg_norm.numpy()
+        full = name in mpc.FULL_SIZE
         for i, aux in enumerate(out["aux_outputs"]):
             blob[f"aux{i}.sem_cls_logits"] = aux["sem_cls_logits"].detach().numpy()
             blob[f"aux{i}.center_normalized"] = aux["center_normalized"].detach().numpy()
+            if full:   # every decoder layer, every head
+                for k in ("size_normalized", "angle_logits", "angle_residual"):
+                    blob[f"aux{i}.{k}"] = aux[k].detach().numpy()
+                blob[f"aux{i}.text_correlation_embedding"] = aux["text_correlation_embedding"].detach().numpy()[:, ::4, ::8]
         blob["loss"] = np.float32(loss.item())
         for k, v in loss_dict.items():
             blob[f"loss_dict.{k}"] = np.float32(float(v))
         blob["state_dict_keys"] = np.array(sorted(k for k in model.state_dict().keys() if "clip_model" not in k))
         g = dict(model.named_parameters())
-        for pname in ("pre_encoder.mlp_module.layer0.conv.weight", "encoder.layers.0.self_attn.in_proj_weight",
-                      "decoder.layers.1.multihead_attn.out_proj.weight", "mlp_heads.center_head.layers.0.weight",
-                      "decoder.norm.weight"):
-            blob[f"grad.{pname}"] = g[pname].grad.numpy()
+        names = GRADS if full else (GRADS[0], GRADS[2], GRADS[7], GRADS[10], GRADS[13])
+        for pname in names:
+            pname = pname.format(last=args.dec_nlayers - 1)
+            blob[f"grad.{pname}"] = thin(g[pname].grad.numpy())
         np.savez_compressed(HERE / f"model_{name}.npz", **blob)
-        print("wrote", name, "loss", float(loss))
+        print("wrote", name, "loss", float(loss), flush=True)
 
 
 if __name__ == "__main__":

@@ -13,21 +13,48 @@ from param_fill import fill_by_name
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
+_SMALL = dict(nqueries=128, preenc_npoints=256, dec_dim=128, dec_nlayers=2, dec_ffn_dim=64,
+              enc_dropout=0.0, dec_dropout=0.0, mlp_dropout=0.0)
+_NODROP = dict(enc_dropout=0.0, dec_dropout=0.0, mlp_dropout=0.0)
+_STAGE2 = dict(if_clip_weak_labels=True, loss_feat_seen_softmax_weakly_loss_with_novel_cate_confi_weight=1.0,
+               confidence_type="clip-max-prob")
+
+# name -> (batch, npoints, args overrides[, extras]); extras: image_hw, text_rows (random unit text rows standing
+# in for the class prompts), seed
 CASES = {
-    "stage1_small": (2, 3000, dict(nqueries=128, preenc_npoints=256, dec_dim=128, dec_nlayers=2, dec_ffn_dim=64,
-                                   enc_dropout=0.0, dec_dropout=0.0, mlp_dropout=0.0)),
-    "stage2_weak": (2, 2500, dict(nqueries=128, preenc_npoints=256, dec_dim=128, dec_nlayers=2, dec_ffn_dim=64,
-                                  enc_dropout=0.0, dec_dropout=0.0, mlp_dropout=0.0, if_clip_weak_labels=True,
-                                  loss_feat_seen_softmax_weakly_loss_with_novel_cate_confi_weight=1.0,
-                                  confidence_type="clip-max-prob")),
+    "stage1_small": (2, 3000, dict(_SMALL)),
+    "stage2_weak": (2, 2500, dict(_SMALL, **_STAGE2)),
+    # the configuration the BASELINE metric is quoted on: 2048 seeds, enc 3 x 256, dec 8 x 512, 256 queries,
+    # 20 000 points (2 scenes so that the CPU reference run stays in minutes)
+    "baseline_full": (2, 20000, dict(_NODROP)),
+    # BASELINE configs[4]: ScanNet shape -- 40 000 points, 1296 x 968 images, 232 text rows (the reference criterion
+    # only admits train_range_max in {10, 37, 232}; 232 = its ScanNet-200 superset), stage-2 losses on
+    "scannet_shape": (2, 40000, dict(_NODROP, image_size_width=1296, image_size_height=968, train_range_max=232,
+                                     test_range_max=232, **_STAGE2),
+                      dict(image_hw=(968, 1296), text_rows=232)),
 }
+FULL_SIZE = ("baseline_full", "scannet_shape")
+
+
+def case(name):
+    c = CASES[name]
+    return c[0], c[1], c[2], (c[3] if len(c) > 3 else {})
+
+
+def text_rows(n: int) -> np.ndarray:
+    """`n` seeded random unit rows (512-d) used as text features when a case sets `text_rows`."""
+    g = np.random.default_rng(4242)
+    t = g.standard_normal((n, 512)).astype(np.float32)
+    return t / np.linalg.norm(t, axis=1, keepdims=True)
+
+
 TINY_CLIP = dict(embed_dim=512, image_resolution=224, vision_layers=2, vision_width=128, vision_patch_size=32,
                  context_length=77, vocab_size=49408, transformer_width=64, transformer_heads=1,
                  transformer_layers=1)
 
 
 def build(name: str, device: str):
-    batch, npoints, over = CASES[name]
+    batch, npoints, over, extra = case(name)
     golden = np.load(GOLDEN / f"model_{name}.npz")
     args = synthetic.make_args(**over)
     cfg = synthetic.SyntheticDatasetConfig(args)
@@ -50,10 +77,12 @@ def build(name: str, device: str):
     model.device = device
     model = model.to(device)
     model.text_features_fg_norm = torch.from_numpy(golden["text_features_fg_norm"]).to(device)
+    model.text_features_fg = model.text_features_fg_norm
     criterion = build_criterion(args, cfg).to(device)
     model.train()
     model.clip_model.eval()
-    inputs = synthetic.to_device(synthetic.make_batch(batch, npoints, seed=5), device)
+    inputs = synthetic.to_device(
+        synthetic.make_batch(batch, npoints, seed=5, image_hw=extra.get("image_hw", (531, 730))), device)
     return args, model, criterion, inputs, golden
 
 
@@ -66,15 +95,27 @@ def run(name: str, device: str):
     return model, out, loss, loss_dict, golden
 
 
-def compare(model, out, loss, loss_dict, golden, rtol, atol, check_grads=True, grad_rtol=None):
-    """Returns a dict name -> max relative error; raises on the first mismatch."""
+def cpu_noise(name: str) -> dict:
+    """fp32-vs-fp32 deviation per golden key (tests/golden/make_cpu_noise.py); {} for the small cases."""
+    import json
+
+    f = GOLDEN / f"model_{name}_cpu_noise.json"
+    return json.loads(f.read_text()) if f.exists() else {}
+
+
+def compare(model, out, loss, loss_dict, golden, rtol, atol, check_grads=True, grad_rtol=None, noise=None):
+    """Returns a dict name -> max relative error; raises on the first mismatch.  `noise` (cpu_noise) widens a
+    gradient's bar to 3 x the deviation another fp32 implementation shows on the same key."""
     errs = {}
+    noise = noise or {}
 
     def chk(key, got, sl=None, rtol=rtol):
         exp = golden[key]
         g = got.detach().float().cpu().numpy()
         if sl is not None:
             g = g[sl]
+        elif g.shape != exp.shape and g.ndim >= 2 and g.size > 65536:
+            g = g[::4, ::4]       # large gradients are stored as a lattice (make_model_golden.thin)
         assert g.shape == exp.shape, (key, g.shape, exp.shape)
         if exp.dtype.kind in "iu":
             assert np.array_equal(g.astype(exp.dtype), exp), key
@@ -96,6 +137,11 @@ def compare(model, out, loss, loss_dict, golden, rtol, atol, check_grads=True, g
     for i, aux in enumerate(out["aux_outputs"]):
         chk(f"aux{i}.sem_cls_logits", aux["sem_cls_logits"])
         chk(f"aux{i}.center_normalized", aux["center_normalized"])
+        for k in ("size_normalized", "angle_logits", "angle_residual"):
+            if f"aux{i}.{k}" in golden.files:
+                chk(f"aux{i}.{k}", aux[k])
+        if f"aux{i}.text_correlation_embedding" in golden.files:
+            chk(f"aux{i}.text_correlation_embedding", aux["text_correlation_embedding"], np.s_[:, ::4, ::8])
     exp_loss = float(golden["loss"])
     errs["loss"] = abs(float(loss) - exp_loss) / abs(exp_loss)
     assert errs["loss"] <= rtol, f"loss {float(loss)} vs {exp_loss}"
@@ -114,5 +160,6 @@ def compare(model, out, loss, loss_dict, golden, rtol, atol, check_grads=True, g
         for k in golden.files:
             if k.startswith("grad."):
                 # gradients cross ~13 layers and train-mode BatchNorm: looser than the forward bar
-                chk(k, params[k[len("grad."):]].grad, rtol=grad_rtol if grad_rtol is not None else 10 * rtol)
+                gr = grad_rtol if grad_rtol is not None else 10 * rtol
+                chk(k, params[k[len("grad."):]].grad, rtol=max(gr, 3.0 * noise.get(k, 0.0)))
     return errs

@@ -17,7 +17,9 @@ def test_model_and_criterion_match_reference_on_cpu(name):
     torch.manual_seed(0)
     with cpu_shims.installed():
         model, out, loss, loss_dict, golden = mpc.run(name, "cpu")
-        errs = mpc.compare(model, out, loss, loss_dict, golden, rtol=2e-4, atol=1e-5)
+        # full-size cases: two fp32 evaluations of the encoder-side gradients differ by up to 5e-3 (make_cpu_noise.py)
+        errs = mpc.compare(model, out, loss, loss_dict, golden, rtol=2e-4, atol=1e-5,
+                           grad_rtol=1e-2 if name in mpc.FULL_SIZE else None)
     worst = max(errs, key=errs.get)
     print(f"{name}: worst {worst} = {errs[worst]:.2e}")
 
