@@ -46,15 +46,24 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     p.add_argument("--nsplit", type=int, default=3, help="bf16 planes per fp32 operand on the tensor-core path")
+    p.add_argument("--num-classes", type=int, default=46, help="text rows (46: SUN RGB-D prompts; 232: ScanNet-200 set)")
+    p.add_argument("--image", default="531x730", help="image height x width (ScanNet shape: 968x1296)")
     return p.parse_args()
 
 
+def image_hw(a):
+    h, w = a.image.lower().split("x")
+    return int(h), int(w)
+
+
 def workload_config(a, world):
-    return {"workload": "CoDA stage-1 train step: PointNet++ SA(20000->2048) + 3DETR enc3/dec8 + CLIP ViT-B/32 "
-                        "alignment (32 crops/scene) + Hungarian losses + AdamW",
+    h, w = image_hw(a)
+    return {"workload": f"CoDA stage-1 train step: PointNet++ SA({a.npoints}->2048) + 3DETR enc3/dec8 + CLIP ViT-B/32 "
+                        "alignment (32 crops/scene) + Hungarian losses + clip + AdamW",
             "npoints": a.npoints, "nqueries": a.nqueries, "batch_per_gpu": a.batch_per_gpu,
             "global_batch": a.batch_per_gpu * world, "parallelism": f"dp{world}",
-            "weights": "random-init (no checkpoints offline)", "num_text_classes": 46,
+            "weights": "random-init (no checkpoints offline)", "num_text_classes": a.num_classes,
+            "image_hw": [h, w],
             "l2": "per-step working set (~2 GB of SA / attention activations) >> 126 MB L2; inputs differ per step"}
 
 
@@ -111,7 +120,8 @@ def cpu_step_rate(a, scenes: int, steps: int, threads: int):
     from coda_neurips2023_b200.models import build_model
 
     torch.set_num_threads(threads)
-    args = synthetic.make_args(nqueries=a.nqueries)
+    h, w = image_hw(a)
+    args = synthetic.make_args(nqueries=a.nqueries, test_range_max=a.num_classes, image_size_width=w, image_size_height=h)
     cfg = synthetic.SyntheticDatasetConfig(args)
     with cpu_step.installed():
         torch.manual_seed(0)
@@ -123,7 +133,8 @@ def cpu_step_rate(a, scenes: int, steps: int, threads: int):
         criterion = build_criterion(args, cfg)
         opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=args.base_lr,
                                 weight_decay=args.weight_decay)
-        batch = {k: torch.from_numpy(v) for k, v in synthetic.make_batch(scenes, a.npoints, seed=0).items()}
+        batch = {k: torch.from_numpy(v)
+                 for k, v in synthetic.make_batch(scenes, a.npoints, seed=0, image_hw=image_hw(a)).items()}
         times = []
         for _ in range(steps):
             t0 = time.perf_counter()
@@ -154,6 +165,8 @@ def run_reference(a):
                                    "incl. CLIP ViT-B/32 on 32 crops/scene; reference PyTorch CPU arithmetic + "
                                    "C restatement of its CUDA-only pointnet2 ops"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_scope": "ONE CPU process on this box's host cores, whatever --gpus says: the CPU path does not shard; "
+                           "compare an N-GPU line with this value as is (it is not scaled by N)",
     }
     print(json.dumps(line), flush=True)
 
@@ -285,9 +298,11 @@ def run_ours(a):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
 
-    args = synthetic.make_args(nqueries=a.nqueries, batchsize_per_gpu=a.batch_per_gpu, ngpus=world)
+    h, w = image_hw(a)
+    args = synthetic.make_args(nqueries=a.nqueries, batchsize_per_gpu=a.batch_per_gpu, ngpus=world,
+                               test_range_max=a.num_classes, image_size_width=w, image_size_height=h)
     cfg = synthetic.SyntheticDatasetConfig(args)
-    torch.manual_seed(0)  # same init on every rank, as DDP's broadcast would give
+    torch.manual_seed(rank)  # per-rank seed as the reference (main.py:982-985); TrainStep broadcasts rank 0's state
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         model, _ = build_model(args, cfg)
@@ -299,7 +314,8 @@ def run_ours(a):
 
     nb = 4  # distinct batches, cycled; seed = rank-dependent (DistributedSampler-like sharding)
     host = [{k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
-             for k, v in synthetic.make_batch(a.batch_per_gpu, a.npoints, seed=100 * rank + i).items()}
+             for k, v in synthetic.make_batch(a.batch_per_gpu, a.npoints, seed=100 * rank + i,
+                                              image_hw=image_hw(a)).items()}
             for i in range(nb)]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0].values())
     resident = [step.to_device(h) for h in host]

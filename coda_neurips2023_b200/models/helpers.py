@@ -1,7 +1,8 @@
 """Building blocks shared by the 3DETR modules (mirror of reference models/helpers.py).
 
-`NORM_DICT["ln"]` is the warp-per-row LayerNorm kernel (same parameters as
-nn.LayerNorm); everything else is plain nn.Modules whose GEMMs run in cuBLAS.
+`NORM_DICT["ln"]` is the warp-per-row LayerNorm kernel (same parameters as nn.LayerNorm);
+GenericMLP keeps the reference's nn.Module tree (parameter paths `layers.{i}`) but executes on
+channels-last rows: tcgen05 GEMMs + one fused BatchNorm/ReLU/Dropout pass per block.
 """
 from __future__ import annotations
 
@@ -87,9 +88,10 @@ class GenericMLP(nn.Module):
                 func(param)
 
     def forward_rows(self, h):
-        """The stack on channels-last rows (N, C_in) -> (N, C_out).  The 1x1 convolutions are GEMMs over
-        the channel dim (ops.linear, tcgen05); BatchNorm1d / ReLU / Dropout act on the same 2-D tensor;
-        a ReLU directly after a dense layer is fused into the GEMM epilogue."""
+        """The stack on channels-last rows (N, C_in) -> (N, C_out).  The 1x1 convolutions are GEMMs over the
+        channel dim (ops.linear, tcgen05); a [BatchNorm1d, ReLU, Dropout] run after a dense layer is ONE fused
+        pass over the rows (ops.bn_act_rows: batch statistics, normalise + ReLU + counter-based dropout); a ReLU
+        directly after a dense layer runs in the GEMM epilogue."""
         mods = list(self.layers)
         i = 0
         while i < len(mods):
@@ -98,9 +100,21 @@ class GenericMLP(nn.Module):
                 fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
                 h = ops.linear(h, mod.weight.reshape(mod.weight.shape[0], -1), mod.bias, relu=fuse)
                 i += 2 if fuse else 1
+            elif isinstance(mod, nn.modules.batchnorm._BatchNorm):
+                j = i + 1
+                relu = j < len(mods) and isinstance(mods[j], nn.ReLU)
+                j += 1 if relu else 0
+                has_drop = j < len(mods) and isinstance(mods[j], nn.Dropout)
+                drop = mods[j].p if has_drop else 0.0
+                j += 1 if has_drop else 0
+                h = ops.bn_act_rows(h, mod, relu, drop, self.training)
+                i = j
+            elif isinstance(mod, nn.Dropout):
+                h = ops.dropout(h, mod.p, self.training)
+                i += 1
             elif isinstance(mod, nn.GroupNorm):
                 raise NotImplementedError("GroupNorm ('ln' on a conv MLP) is not used on the CoDA path")
-            else:                                  # BatchNorm1d on (N, C), ReLU, Dropout, LayerNorm
+            else:                                  # ReLU after a norm-less dense layer, LayerNorm
                 h = mod(h)
                 i += 1
         return h

@@ -216,7 +216,10 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
             try:
                 from ..clip.tokenizer import tokenize
                 tokens = tokenize(prompts).to(self.device)
-            except FileNotFoundError:
+            except FileNotFoundError as e:
+                if os.path.exists(ckpt):
+                    raise RuntimeError("a real CLIP checkpoint was loaded but the BPE vocabulary of the tokenizer is "
+                                       f"missing ({e}): refusing to substitute random text features") from e
                 tokens = None
         self.all_classes_keys = prompts
         with torch.no_grad():
@@ -224,6 +227,11 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
                 feats = self.clip_model.encode_text(tokens).to(torch.float32)
             else:
                 # synthetic run: random unit rows stand in for the text embeddings
+                if os.path.exists(ckpt):
+                    raise RuntimeError(f"CLIP checkpoint {ckpt} found but the class list / tokenizer vocabulary is not: "
+                                       "the text features would be meaningless")
+                warnings.warn("class prompts unavailable: RANDOM unit rows stand in for the CLIP text features "
+                              "(throughput / parity runs only; class scores and weak labels are meaningless)")
                 n = args.test_range_max if self.if_clip_more_prompts else args.train_range_max
                 g = torch.Generator().manual_seed(1234)
                 feats = torch.randn(n, self.clip_model.visual.output_dim, generator=g).to(self.device)

@@ -129,11 +129,11 @@ class TransformerEncoderLayer(nn.Module):
         else:
             qk = src2 + pos
             attn = self.self_attn(qk, qk, src2, attn_mask=src_mask, key_padding_mask=src_key_padding_mask)[0]
-        src = src + self.dropout1(attn)
+        src = ops.dropout_add(attn, src, self.dropout1.p, self.training)
         if self.use_ffn:
             src2 = self.norm2(src)
-            src2 = self.linear2(self.dropout(_ffn_hidden(self, src2)))
-            src = src + self.dropout2(src2)
+            src2 = self.linear2(ops.dropout(_ffn_hidden(self, src2), self.dropout.p, self.training))
+            src = ops.dropout_add(src2, src, self.dropout2.p, self.training)
         if return_attn_weights:
             return src, None
         return src
@@ -141,11 +141,10 @@ class TransformerEncoderLayer(nn.Module):
     def forward_post(self, src, src_mask=None, src_key_padding_mask=None, pos=None):
         qk = self.with_pos_embed(src, pos)
         src2 = self.self_attn(qk, qk, src, attn_mask=src_mask, key_padding_mask=src_key_padding_mask)[0]
-        src = src + self.dropout1(src2)
-        src = self.norm1(src)
+        src = self.norm1(ops.dropout_add(src2, src, self.dropout1.p, self.training))
         if self.use_ffn:
-            src2 = self.linear2(self.dropout(_ffn_hidden(self, src)))
-            src = self.norm2(src + self.dropout2(src2))
+            src2 = self.linear2(ops.dropout(_ffn_hidden(self, src), self.dropout.p, self.training))
+            src = self.norm2(ops.dropout_add(src2, src, self.dropout2.p, self.training))
         return src
 
     def forward(self, src, src_mask=None, src_key_padding_mask=None, pos=None, return_attn_weights=False):
@@ -248,14 +247,14 @@ class TransformerDecoderLayer(nn.Module):
         tgt2 = self.norm1(tgt)
         qk = self.with_pos_embed(tgt2, query_pos)
         tgt2 = self.self_attn(qk, qk, tgt2, attn_mask=tgt_mask, key_padding_mask=tgt_key_padding_mask)[0]
-        tgt = tgt + self.dropout1(tgt2)
+        tgt = ops.dropout_add(tgt2, tgt, self.dropout1.p, self.training)
         tgt2 = self.norm2(tgt)
         tgt2 = self.multihead_attn(self.with_pos_embed(tgt2, query_pos), memory_key, memory,
                                    attn_mask=memory_mask, key_padding_mask=memory_key_padding_mask)[0]
-        tgt = tgt + self.dropout2(tgt2)
+        tgt = ops.dropout_add(tgt2, tgt, self.dropout2.p, self.training)
         tgt2 = self.norm3(tgt)
-        tgt2 = self.linear2(self.dropout(_ffn_hidden(self, tgt2)))
-        tgt = tgt + self.dropout3(tgt2)
+        tgt2 = self.linear2(ops.dropout(_ffn_hidden(self, tgt2), self.dropout.p, self.training))
+        tgt = ops.dropout_add(tgt2, tgt, self.dropout3.p, self.training)
         return tgt, None
 
     def forward_post(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
@@ -265,12 +264,12 @@ class TransformerDecoderLayer(nn.Module):
             memory_key = self.with_pos_embed(memory, pos)
         qk = self.with_pos_embed(tgt, query_pos)
         tgt2 = self.self_attn(qk, qk, tgt, attn_mask=tgt_mask, key_padding_mask=tgt_key_padding_mask)[0]
-        tgt = self.norm1(tgt + self.dropout1(tgt2))
+        tgt = self.norm1(ops.dropout_add(tgt2, tgt, self.dropout1.p, self.training))
         tgt2 = self.multihead_attn(self.with_pos_embed(tgt, query_pos), memory_key, memory,
                                    attn_mask=memory_mask, key_padding_mask=memory_key_padding_mask)[0]
-        tgt = self.norm2(tgt + self.dropout2(tgt2))
-        tgt2 = self.linear2(self.dropout(_ffn_hidden(self, tgt)))
-        tgt = self.norm3(tgt + self.dropout3(tgt2))
+        tgt = self.norm2(ops.dropout_add(tgt2, tgt, self.dropout2.p, self.training))
+        tgt2 = self.linear2(ops.dropout(_ffn_hidden(self, tgt), self.dropout.p, self.training))
+        tgt = self.norm3(ops.dropout_add(tgt2, tgt, self.dropout3.p, self.training))
         return tgt, None
 
     def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,

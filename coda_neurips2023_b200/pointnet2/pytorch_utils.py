@@ -137,6 +137,9 @@ class SharedMLP(nn.Sequential):
         pools itself."""
         from .. import sa_mlp
 
+        if any(isinstance(m, nn.SyncBatchNorm) for m in self.modules()):
+            raise NotImplementedError("SyncBatchNorm inside SharedMLP: this package runs per-GPU BatchNorm "
+                                      "(DESIGN.md section 7) -- do not call convert_sync_batchnorm on the model")
         if x.dim() != 4 or not x.is_cuda or not torch.is_grad_enabled():
             return None
         blocks = []

