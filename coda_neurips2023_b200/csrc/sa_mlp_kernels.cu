@@ -150,6 +150,56 @@ __global__ void bn_stats_finalize_kernel(int nblocks, long long rows, int c, con
   if (running_var) running_var[ch] = (1.0f - momentum) * running_var[ch] + momentum * (float)(var * (n / fmax(n - 1.0, 1.0)));
 }
 
+// finalisation of per-CTA partials written by a GEMM epilogue (coda_gemm_a32 col_stats): statistics + running
+// buffers as above, plus the folded per-channel affine map of BatchNorm: scale = gamma * invstd,
+// shift = beta - mean * scale (what the next GEMM's prologue applies), zero-padded up to cpad
+__global__ void bn_stats_finalize_affine_kernel(int nblocks, long long rows, int c, int cpad,
+                                                const float *__restrict__ partial, float eps, float momentum,
+                                                float *running_mean, float *running_var, const float *__restrict__ gamma,
+                                                const float *__restrict__ beta, float *__restrict__ mean,
+                                                float *__restrict__ invstd, float *__restrict__ scale,
+                                                float *__restrict__ shift) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= cpad) return;
+  if (ch >= c) {
+    if (scale) { scale[ch] = 0.f; shift[ch] = 0.f; }
+    return;
+  }
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    s += (double)partial[(size_t)b * 2 * c + ch];
+    q += (double)partial[(size_t)b * 2 * c + c + ch];
+  }
+  const double n = (double)rows, m = s / n;
+  double var = q / n - m * m;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)eps));
+  mean[ch] = (float)m;
+  invstd[ch] = is;
+  if (running_mean) running_mean[ch] = (1.0f - momentum) * running_mean[ch] + momentum * (float)m;
+  if (running_var) running_var[ch] = (1.0f - momentum) * running_var[ch] + momentum * (float)(var * (n / fmax(n - 1.0, 1.0)));
+  if (scale) {
+    const float sc = gamma[ch] * is;
+    scale[ch] = sc;
+    shift[ch] = beta[ch] - (float)m * sc;
+  }
+}
+// BatchNorm-backward coefficients of the GEMM prologue: dy = [z > 0] * scale * d + alpha * y + beta
+//   alpha = -scale * invstd * s2 / N,   beta = -scale * s1 / N - alpha * mean
+__global__ void bn_bwd_coefs_kernel(int c, int cpad, long long rows, const float *__restrict__ mean,
+                                    const float *__restrict__ invstd, const float *__restrict__ gamma,
+                                    const float *__restrict__ s1, const float *__restrict__ s2,
+                                    float *__restrict__ alpha, float *__restrict__ beta) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= cpad) return;
+  if (ch >= c) { alpha[ch] = 0.f; beta[ch] = 0.f; return; }
+  const float inv_n = 1.0f / (float)rows;
+  const float sc = gamma[ch] * invstd[ch];
+  const float a = -sc * invstd[ch] * (s2[ch] * inv_n);
+  alpha[ch] = a;
+  beta[ch] = -sc * (s1[ch] * inv_n) - a * mean[ch];
+}
+
 // column sums only (bias gradients: db = sum over rows of dY); partial[blk][c]
 __global__ void __launch_bounds__(THREADS)
 colsum_partial_kernel(long long rows, int c, const float *__restrict__ x, float *__restrict__ partial) {
@@ -423,6 +473,41 @@ int coda_bn_rows_stats(long long rows, int c, const float *y, float eps, float m
   bn_stats_partial_kernel<<<grid, THREADS, 0, s>>>(rows, c, y, scratch);
   bn_stats_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>((int)grid, rows, c, scratch, eps, momentum, running_mean,
                                                            running_var, mean, invstd);
+  return coda::launch_status();
+}
+
+int coda_bn_rows_stats_affine(long long rows, int c, const float *y, float eps, float momentum, float *running_mean,
+                               float *running_var, const float *gamma, const float *beta, float *mean, float *invstd,
+                               float *scale, float *shift, float *scratch, void *stream) {
+  if (rows <= 0 || !channels_ok(c) || !y || !mean || !invstd || !scratch || !gamma || !beta || !scale || !shift)
+    return CODA_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = grid_for(rows, c);
+  bn_stats_partial_kernel<<<grid, THREADS, 0, s>>>(rows, c, y, scratch);
+  const int cpad = (c + 63) / 64 * 64;
+  bn_stats_finalize_affine_kernel<<<(cpad + 127) / 128, 128, 0, s>>>((int)grid, rows, c, cpad, scratch, eps, momentum,
+                                                                    running_mean, running_var, gamma, beta, mean,
+                                                                    invstd, scale, shift);
+  return coda::launch_status();
+}
+
+int coda_bn_stats_finalize(int nblocks, long long rows, int c, const float *partial, float eps, float momentum,
+                           float *running_mean, float *running_var, const float *gamma, const float *beta,
+                           float *mean, float *invstd, float *scale, float *shift, void *stream) {
+  if (nblocks <= 0 || rows <= 0 || c <= 0 || !partial || !mean || !invstd) return CODA_EINVAL;
+  if ((scale != nullptr) != (shift != nullptr) || (scale && (!gamma || !beta))) return CODA_EINVAL;
+  const int cpad = (c + 63) / 64 * 64;
+  bn_stats_finalize_affine_kernel<<<(cpad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      nblocks, rows, c, cpad, partial, eps, momentum, running_mean, running_var, gamma, beta, mean, invstd, scale, shift);
+  return coda::launch_status();
+}
+
+int coda_bn_bwd_coefs(int c, long long rows, const float *mean, const float *invstd, const float *gamma,
+                      const float *s1, const float *s2, float *alpha, float *beta, void *stream) {
+  if (c <= 0 || rows <= 0 || !mean || !invstd || !gamma || !s1 || !s2 || !alpha || !beta) return CODA_EINVAL;
+  const int cpad = (c + 63) / 64 * 64;
+  bn_bwd_coefs_kernel<<<(cpad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c, cpad, rows, mean, invstd, gamma, s1, s2,
+                                                                           alpha, beta);
   return coda::launch_status();
 }
 

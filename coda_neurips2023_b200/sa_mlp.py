@@ -75,8 +75,61 @@ def _stats(y: torch.Tensor, bn: nn.modules.batchnorm._BatchNorm):
     return mean, invstd
 
 
+def _stats_affine(y: torch.Tensor, bn, gamma, beta):
+    """Batch statistics of y (rows, c) + the folded BatchNorm map (scale, shift) for the next GEMM's prologue."""
+    rows, c = y.shape
+    momentum, track = _bn_bookkeeping(bn)
+    dev = y.device
+    cpad = ops._pad64(c)
+    mean = torch.empty(c, dtype=torch.float32, device=dev)
+    invstd = torch.empty(c, dtype=torch.float32, device=dev)
+    scale = torch.empty(cpad, dtype=torch.float32, device=dev)
+    shift = torch.empty(cpad, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = lib().coda_bn_rows_stats_affine(_ll(rows), _i(c), ptr(y), _f(bn.eps), _f(momentum),
+                                             ptr(bn.running_mean if track else None),
+                                             ptr(bn.running_var if track else None), ptr(gamma), ptr(beta), ptr(mean),
+                                             ptr(invstd), ptr(scale), ptr(shift), ptr(_scratch(c, dev)), stream_of(y))
+    check(st, "bn_rows_stats_affine")
+    return mean, invstd, scale, shift
+
+
+def _bn_bookkeeping(bn):
+    momentum = 0.0 if bn.momentum is None else float(bn.momentum)
+    track = bn.track_running_stats and bn.running_mean is not None
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            raise NotImplementedError("cumulative-average BatchNorm momentum is not on the CoDA path")
+    return momentum, track
+
+
+def _stats_from_partials(partials: torch.Tensor, rows: int, bn, gamma, beta, want_affine: bool):
+    """Finalise the column-sum partials a GEMM epilogue wrote (no pass over the activation)."""
+    nblocks, _, c = partials.shape
+    momentum, track = _bn_bookkeeping(bn)
+    dev = partials.device
+    mean = torch.empty(c, dtype=torch.float32, device=dev)
+    invstd = torch.empty(c, dtype=torch.float32, device=dev)
+    scale = shift = None
+    if want_affine:
+        scale = torch.empty(ops._pad64(c), dtype=torch.float32, device=dev)
+        shift = torch.empty(ops._pad64(c), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = lib().coda_bn_stats_finalize(_i(nblocks), _ll(rows), _i(c), ptr(partials), _f(bn.eps), _f(momentum),
+                                          ptr(bn.running_mean if track else None),
+                                          ptr(bn.running_var if track else None), ptr(gamma), ptr(beta), ptr(mean),
+                                          ptr(invstd), ptr(scale), ptr(shift), stream_of(partials))
+    check(st, "bn_stats_finalize")
+    return mean, invstd, scale, shift
+
+
 class _SharedMLPMax(torch.autograd.Function):
-    """forward(x_rows (R, C0), group, nsplit, bns, W0, g0, b0, W1, g1, b1, ...) -> pooled (R / group, C_last)"""
+    """forward(x_rows (R, C0), group, nsplit, bns, W0, g0, b0, W1, g1, b1, ...) -> pooled (R / group, C_last)
+
+    Forward data flow (HBM): y_l is written ONCE as fp32 by GEMM l, whose epilogue also produces the BatchNorm
+    statistics of y_l; GEMM l+1 reads y_l in place and applies BatchNorm + ReLU + the bf16 split in its prologue
+    (ops.gemm_a32, CODA_A32_AFFINE_RELU).  No operand planes, no separate statistics pass."""
 
     @staticmethod
     def forward(ctx, x, group, nsplit, bns, *params):
@@ -84,40 +137,37 @@ class _SharedMLPMax(torch.autograd.Function):
         nl = len(bns)
         rows, c0 = x.shape
         dev = x.device
-        ys, means, invstds, acts = [], [], [], []
+        ys, means, invstds, scales, shifts = [], [], [], [], []
         small_k = c0 <= 8
-        cur = None
+        scale = shift = None
         with torch.cuda.device(dev):
             for li in range(nl):
                 w, gamma, beta = params[3 * li: 3 * li + 3]
                 cout, cin = w.shape
+                last = li == nl - 1
                 if li == 0 and small_k:
                     y = torch.empty((rows, cout), dtype=torch.float32, device=dev)
                     check(L.coda_rows_linear_small_k(_ll(rows), _i(cin), _i(cout), ptr(x), ptr(w.contiguous()), ptr(y),
                                                      stream_of(x)), "rows_linear_small_k")
+                    mean, invstd, scale, shift = _stats_affine(y, bns[li], gamma, beta)
                 else:
+                    wp = ops._packed_weight(w, False, nsplit)
                     if li == 0:
-                        cur = ops.pack_split(x, rows, c0, c0, 1, nsplit)
-                    y = ops.gemm_nt(cur, ops._packed_weight(w, False, nsplit), rows, cout)[0]
-                mean, invstd = _stats(y, bns[li])
-                ys.append(y); means.append(mean); invstds.append(invstd)
-                if li < nl - 1:
-                    nxt = torch.empty((nsplit, 1, rows, cout), dtype=torch.bfloat16, device=dev)
-                    check(L.coda_bn_relu_pack_rows(_ll(rows), _i(cout), _i(nsplit), ptr(y), ptr(mean), ptr(invstd),
-                                                   ptr(gamma), ptr(beta), ptr(nxt), stream_of(x)), "bn_relu_pack_rows")
-                    acts.append(cur)      # operand planes of THIS layer's input (None for the tiny-K layer)
-                    cur = nxt
-                else:
-                    acts.append(cur)
+                        y, part = ops.gemm_a32(x, wp, cout, want_stats=True)
+                    else:
+                        y, part = ops.gemm_a32(ys[-1], wp, cout, mode=ops.A32_AFFINE_RELU, scale=scale, shift=shift,
+                                               want_stats=True)
+                    mean, invstd, scale, shift = _stats_from_partials(part, rows, bns[li], gamma, beta, True)
+                ys.append(y); means.append(mean); invstds.append(invstd); scales.append(scale); shifts.append(shift)
+                if last:
                     groups = rows // group
                     pooled = torch.empty((groups, cout), dtype=torch.float32, device=dev)
                     argmax = torch.empty((groups, cout), dtype=torch.uint8, device=dev)
                     check(L.coda_bn_relu_maxpool_rows(_ll(groups), _i(group), _i(cout), ptr(y), ptr(mean), ptr(invstd),
                                                       ptr(gamma), ptr(beta), ptr(pooled), ptr(argmax), stream_of(x)),
                           "bn_relu_maxpool_rows")
-        ctx.nl, ctx.group, ctx.small_k = nl, group, small_k
-        ctx.acts = acts                       # bf16 planes: not autograd inputs, kept by reference
-        ctx.save_for_backward(x, argmax, *ys, *means, *invstds, *params)
+        ctx.nl, ctx.group, ctx.small_k, ctx.nsplit = nl, group, small_k, nsplit
+        ctx.save_for_backward(x, argmax, *ys, *means, *invstds, *scales, *shifts, *params)
         ctx.mark_non_differentiable(argmax)
         return pooled, argmax
 
@@ -130,7 +180,9 @@ class _SharedMLPMax(torch.autograd.Function):
         ys = saved[2: 2 + nl]
         means = saved[2 + nl: 2 + 2 * nl]
         invstds = saved[2 + 2 * nl: 2 + 3 * nl]
-        params = saved[2 + 3 * nl:]
+        scales = saved[2 + 3 * nl: 2 + 4 * nl]
+        shifts = saved[2 + 4 * nl: 2 + 5 * nl]
+        params = saved[2 + 5 * nl:]
         rows = x.shape[0]
         dev = x.device
         ns = BACKWARD_PLANES
@@ -146,7 +198,8 @@ class _SharedMLPMax(torch.autograd.Function):
                 s1 = torch.empty(cout, dtype=torch.float32, device=dev)
                 s2 = torch.empty(cout, dtype=torch.float32, device=dev)
                 scratch = _scratch(cout, dev)
-                if li == nl - 1:
+                pooled_form = li == nl - 1
+                if pooled_form:
                     check(L.coda_bn_relu_bwd_reduce_pooled(_ll(rows // group), _i(group), _i(cout), ptr(y), ptr(dpooled),
                                                            ptr(argmax), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta),
                                                            ptr(s1), ptr(s2), ptr(scratch), stream_of(x)),
@@ -170,16 +223,30 @@ class _SharedMLPMax(torch.autograd.Function):
                                                      stream_of(x)), "bn_relu_bwd_small_k")
                     grads[0] = dw
                     break
-                dy = torch.empty((ns, 1, rows, cout), dtype=torch.bfloat16, device=dev)
-                pooled_form = li == nl - 1
-                check(L.coda_bn_relu_bwd_pack(_ll(rows), _i(cout), _i(ns), ptr(y), ptr(None if pooled_form else dz),
-                                              ptr(dpooled if pooled_form else None), ptr(argmax if pooled_form else None),
-                                              _i(group), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(s1), ptr(s2),
-                                              ptr(dy), stream_of(x)), "bn_relu_bwd_pack")
-                a_prev = ctx.acts[li]
-                grads[3 * li] = ops.gemm_tn(dy, a_prev[:ns], cout, cin)              # dW = dy^T a_{l-1}
+                # BatchNorm(+ReLU) backward as a GEMM prologue: dy = [z > 0] * scale * d + alpha * y + beta
+                cpad = ops._pad64(cout)
+                alpha = torch.empty(cpad, dtype=torch.float32, device=dev)
+                bcoef = torch.empty(cpad, dtype=torch.float32, device=dev)
+                check(L.coda_bn_bwd_coefs(_i(cout), _ll(rows), ptr(mean), ptr(invstd), ptr(gamma), ptr(s1), ptr(s2),
+                                          ptr(alpha), ptr(bcoef), stream_of(x)), "bn_bwd_coefs")
+                pro = dict(a_scale=scales[li], a_shift=shifts[li], a_alpha=alpha, a_beta=bcoef)
+                if pooled_form:
+                    mode, a2 = ops.A32_BN_BWD_POOLED, dpooled
+                    extra = dict(argmax=argmax, group=group)
+                else:
+                    mode, a2, extra = ops.A32_BN_BWD, dz, {}
+                # dW = dy^T a_{l-1}: both operands are read as fp32 rows; a_{l-1} = relu(bn(y_{l-1})) (or x)
+                if li > 0:
+                    grads[3 * li] = ops.gemm_tn32(y, ys[li - 1], a_mode=mode, a2=a2, b_mode=ops.A32_AFFINE_RELU,
+                                                  b_scale=scales[li - 1], b_shift=shifts[li - 1], **pro, **extra)
+                else:
+                    grads[3 * li] = ops.gemm_tn32(y, x, a_mode=mode, a2=a2, **pro, **extra)
                 if li > 0 or ctx.needs_input_grad[0]:
-                    dz = ops.gemm_nt(dy, ops._packed_weight(w, True, ns), rows, cin)[0]  # gradient of the layer input
+                    # dz_{l-1} = dy W_l: the forward weight planes as an MN-major operand
+                    dz_new = ops.gemm_a32(y, ops._packed_weight(w, False, ctx.nsplit), cin, mode=mode, scale=scales[li],
+                                          shift=shifts[li], alpha=alpha, beta=bcoef, a2=a2, b_mn=True, nsplit=ns,
+                                          **extra)
+                    dz = dz_new
                     if li == 0:
                         dx = dz
         return (dx, None, None, None, *grads)

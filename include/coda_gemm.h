@@ -73,6 +73,57 @@ int coda_gemm_nt_res(int nsplit, int is_fp16, int batch, int m, int n, int kpad,
 int coda_gemm_tn(int nsplit, int mc, int m, int n, const void *a, long long a_plane_stride, int lda,
                  const void *b, long long b_plane_stride, int ldb, float *c, long long ldc, void *stream);
 
+/*
+ * GEMM with an FP32 A operand and an in-kernel prologue (csrc/gemm_a32_sm100.cu):
+ *
+ *     C (m, n) fp32 = T(A) (m, k) @ B^T  (+ bias) (ReLU)
+ *
+ * A is read as fp32 rows (row stride lda, multiple of 4 elements, 16-byte aligned base) by TMA, transformed
+ * element-wise by T, split into `nsplit` (2 or 3) bf16 planes and handed to the tensor cores through tensor
+ * memory -- no packed copy of A exists in HBM.  T (`a_mode`), with per-k vectors padded to a multiple of 64:
+ *   CODA_A32_PLAIN          T = a                                   (every nn.Linear / 1x1 conv on the path)
+ *   CODA_A32_AFFINE_RELU    T = relu(a * scale[k] + shift[k])       (BatchNorm(batch stats) + ReLU of the previous
+ *                                                                    layer: pytorch_utils.py:8-33 SharedMLP blocks)
+ *   CODA_A32_BN_BWD         T = [a * scale + shift > 0] * scale * a2 + a * alpha + beta
+ *                               a = pre-BN activation, a2 (m, k) = gradient of relu(bn(a)): the BatchNorm+ReLU
+ *                               backward folded into the input-gradient GEMM  dX = dY W
+ *   CODA_A32_BN_BWD_POOLED  same, the gradient comes from a max-pooled output: a2 = dpooled (m / group, k),
+ *                               argmax (m / group, k) uint8 = row within the group that produced the maximum
+ * B: bf16 planes as produced by coda_pack_split_bf16, either K-major [n][b_ld] (b_mn = 0, b_ld >= pad64(k)) or
+ * "MN-major" [k][b_ld] (b_mn = 1, b_ld >= n: the forward weight planes reused for the input gradient).
+ * col_stats: NULL, or [coda_gemm_a32_grid(m, n)][2][n] floats that receive per-CTA partial column sums and sums of
+ * squares of C (BatchNorm statistics of the layer just computed; n <= 512), to be finalised by
+ * coda_bn_stats_finalize (coda_sa_mlp.h).
+ */
+#define CODA_A32_PLAIN 0
+#define CODA_A32_AFFINE_RELU 1
+#define CODA_A32_BN_BWD 2
+#define CODA_A32_BN_BWD_POOLED 3
+int coda_gemm_a32_grid(int m, int n);
+int coda_gemm_a32(int nsplit, int m, int n, int k, const float *a, long long lda, int a_mode, const float *a_scale,
+                  const float *a_shift, const float *a_alpha, const float *a_beta, const float *a2, long long lda2,
+                  const unsigned char *a_argmax, int a_group, const void *b_planes, long long b_plane_stride,
+                  int b_ld, int b_mn, const float *bias, int act, float *c, long long ldc, float *col_stats,
+                  void *stream);
+
+/*
+ * Weight-gradient form on fp32 rows with in-kernel prologues (csrc/gemm_tn32_sm100.cu):
+ *
+ *     C (m, n) fp32 = sum_r TA(A)[r][:m]^T TB(B)[r][:n],   A (rows, m) with row stride lda, B (rows, n) with ldb
+ *
+ * TA: CODA_A32_PLAIN | CODA_A32_BN_BWD (a2 (rows, m) = gradient of relu(bn(a)), per-column scale / shift / alpha /
+ * beta) | CODA_A32_BN_BWD_POOLED (a2 = dpooled (rows / group, m), argmax);  TB: CODA_A32_PLAIN |
+ * CODA_A32_AFFINE_RELU (relu(b * b_scale + b_shift): the BatchNorm + ReLU that produced this layer's input).
+ * Two bf16 planes per operand (gradient precision).  m, n, lda, ldb, ldc multiples of 4; per-column vectors have
+ * at least m (resp. n) entries.  Split-K over all SMs; C is fully overwritten.
+ * Replaces, for dW = dY^T X of every 1x1 conv of the shared MLP (pytorch_utils.py:8-33 backward), the chain
+ * "BatchNorm backward -> packed dY planes; packed X planes; packed TN GEMM".
+ */
+int coda_gemm_tn32(long long rows, int m, int n, const float *a, long long lda, int a_mode, const float *a_scale,
+                   const float *a_shift, const float *a_alpha, const float *a_beta, const float *a2, long long lda2,
+                   const unsigned char *a_argmax, int a_group, const float *b, long long ldb, int b_mode,
+                   const float *b_scale, const float *b_shift, float *c, long long ldc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,29 @@ int coda_rows_linear_small_k(long long rows, int cin, int cout, const float *x, 
 int coda_bn_rows_stats(long long rows, int c, const float *y, float eps, float momentum, float *running_mean,
                        float *running_var, float *mean, float *invstd, float *scratch, void *stream);
 
+/* As coda_bn_rows_stats, plus the folded affine map scale = gamma * invstd, shift = beta - mean * scale
+ * (zero-padded to a multiple of 64 entries) for the next GEMM's CODA_A32_AFFINE_RELU prologue. */
+int coda_bn_rows_stats_affine(long long rows, int c, const float *y, float eps, float momentum, float *running_mean,
+                               float *running_var, const float *gamma, const float *beta, float *mean, float *invstd,
+                               float *scale, float *shift, float *scratch, void *stream);
+
+/*
+ * The same statistics from per-CTA partial column sums partial[nblocks][2][c] (sum | sum of squares) that a GEMM
+ * epilogue wrote (coda_gemm_a32 `col_stats`): no pass over the activation at all.  Optionally also emits the folded
+ * affine map of BatchNorm, scale[c] = gamma * invstd, shift[c] = beta - mean * scale (zero-padded to a multiple of
+ * 64 entries), which the next GEMM applies in its A prologue (CODA_A32_AFFINE_RELU).
+ */
+int coda_bn_stats_finalize(int nblocks, long long rows, int c, const float *partial, float eps, float momentum,
+                           float *running_mean, float *running_var, const float *gamma, const float *beta,
+                           float *mean, float *invstd, float *scale, float *shift, void *stream);
+/*
+ * Per-channel coefficients of the BatchNorm(+ReLU) backward as a GEMM prologue (CODA_A32_BN_BWD*):
+ *   dy = [y * scale + shift > 0] * scale * d + alpha * y + beta,
+ *   alpha = -scale * invstd * s2 / rows,  beta = -scale * s1 / rows - alpha * mean   (padded to a multiple of 64)
+ */
+int coda_bn_bwd_coefs(int c, long long rows, const float *mean, const float *invstd, const float *gamma,
+                      const float *s1, const float *s2, float *alpha, float *beta, void *stream);
+
 /*
  * out[c] = sum over rows of x (rows, c): the bias gradient of a Linear (db = column sums of dY); deterministic
  * two-stage reduction; scratch as for coda_bn_rows_stats.   replaces `dy.sum(dim=0)` in the Linear backward.
