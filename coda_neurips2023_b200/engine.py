@@ -292,7 +292,10 @@ class TrainStep:
         one value of this key only."""
         m = self.model
         late = int(curr_epoch) >= 540
-        return (late and getattr(m, "if_select_box_by_objectness", False), late and getattr(m, "if_keep_box", False))
+        discover = (getattr(m, "online_nms_update_save_novel_label_clip_driven_with_cate_confidence", False)
+                    and int(curr_epoch) % max(int(getattr(m, "online_nms_update_save_epoch", 1)), 1) == 0)
+        return (late and getattr(m, "if_select_box_by_objectness", False), late and getattr(m, "if_keep_box", False),
+                discover)
 
     # ------------------------------------------------------------------ state that a dry run must not change
     def _volatile(self):
@@ -407,9 +410,19 @@ class TrainStep:
             for k, v in batch.items():
                 if isinstance(v, torch.Tensor):
                     self.static_batch[k].copy_(v, non_blocking=True)
+                elif k == "pseudo_box_path":
+                    self.static_batch[k] = v
             self.graph.replay()
-            return self.static_out
-        return self._body(batch, curr_epoch)
+            out = self.static_out
+        else:
+            out = self._body(batch, curr_epoch)
+        if self._branch(curr_epoch)[2]:
+            # stage-2 discovery epoch: the pseudo-label rows of this step go to the scenes' .npy files now (the one
+            # device->host copy of the path; every other epoch the step stays free of host synchronisation)
+            if self.graph is not None and getattr(self.model, "_pending_pseudo", None) is not None:
+                self.model._pending_pseudo["paths"] = batch.get("pseudo_box_path")
+            self.model.flush_pseudo_labels()
+        return out
 
     def _body(self, batch: dict, curr_epoch: float):
         from . import attention_launch

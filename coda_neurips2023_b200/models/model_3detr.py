@@ -191,6 +191,7 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
         self.dataset_name = "scannet" if args.dataset_name.find("scannet") != -1 else "sunrgbd"
         self.if_clip_weak_labels = getattr(args, "if_clip_weak_labels", False)
         self.if_accumulate_former_pseudo_labels = getattr(args, "if_accumulate_former_pseudo_labels", False)
+        self._pending_pseudo = None
 
     # ------------------------------------------------------------------ CLIP side
     def _build_clip(self, args, dataset_config):
@@ -385,34 +386,46 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
                                   "variable number of crops per scene; not on the B200 path yet")
 
     @torch.no_grad()
-    def get_predicted_box_clip_embedding(self, inputs, outputs, thres_obj=0.05, if_use_gt_box=False,
-                                         if_expand_box=False, if_padding_input=True, test=False, curr_epoch=-1):
-        """CLIP image embeddings of the crops under `distillation_box_num` predicted boxes per
-        scene -> outputs['gt_text_correlation_embedding'(_mask)] (+ weak labels).
-        Same semantics as reference :902-1210, without host synchronisation."""
+    def _boxes_in_image(self, inputs, outputs):
+        """Every predicted box projected into the image: int32 (B, Q, 4) [xmin, ymin, xmax, ymax] (the reference's
+        `int(torch.min/max(.))` truncation of non-negative fp64 values) and the boxes that are usable as crops
+        (non-degenerate, in front of the camera, non-zero size; reference :1034-1051)."""
         corners = outputs["box_corners_xyz"].detach()
-        bsz, nq = corners.shape[0], corners.shape[1]
-        dev = corners.device
         uv, depth = _project_corners_to_image(corners, inputs)          # (B, Q, 8, 2) f64
-        sel = self._select_boxes(outputs["objectness_prob"], curr_epoch)  # (B, S)
-        take = lambda t: torch.gather(t, 1, sel.view(bsz, -1, *([1] * (t.dim() - 2))).expand(-1, -1, *t.shape[2:]))  # noqa: E731
-        uv_s, depth_s = take(uv), take(depth)
-        size_s = take(outputs["size_unnormalized"].detach())
-        # int(torch.min/max(.)) of the reference: truncation of non-negative fp64 values
-        xmin = uv_s[..., 0].amin(-1).to(torch.int32)
-        ymin = uv_s[..., 1].amin(-1).to(torch.int32)
-        xmax = uv_s[..., 0].amax(-1).to(torch.int32)
-        ymax = uv_s[..., 1].amax(-1).to(torch.int32)
-        valid = ((xmax - xmin) > 0) & ((ymax - ymin) > 0) & (depth_s.amin(-1) >= 0) & \
-                ~(size_s.amax(-1) < 1e-16)
-        boxes = torch.stack((xmin, ymin, xmax, ymax), dim=-1).reshape(-1, 4).contiguous()
-        scene = torch.arange(bsz, device=dev, dtype=torch.int32).repeat_interleave(sel.shape[1])
-        crops = ops.crop_resize_normalize(inputs["input_image"], scene, boxes, valid.reshape(-1),
-                                          self.clip_resolution, dtype=self.clip_model.dtype)
+        xmin = uv[..., 0].amin(-1).to(torch.int32)
+        ymin = uv[..., 1].amin(-1).to(torch.int32)
+        xmax = uv[..., 0].amax(-1).to(torch.int32)
+        ymax = uv[..., 1].amax(-1).to(torch.int32)
+        valid = ((xmax - xmin) > 0) & ((ymax - ymin) > 0) & (depth.amin(-1) >= 0) & \
+                ~(outputs["size_unnormalized"].detach().amax(-1) < 1e-16)
+        return torch.stack((xmin, ymin, xmax, ymax), dim=-1), valid
+
+    @torch.no_grad()
+    def _clip_embed_boxes(self, inputs, boxes, valid, sel):
+        """CLIP image embeddings of the crops under boxes[b, sel[b, s]] -> (B, S, D) fp32 (garbage where invalid)."""
+        bsz, nsel = sel.shape
+        bx = torch.gather(boxes, 1, sel.unsqueeze(-1).expand(-1, -1, 4)).reshape(-1, 4).contiguous()
+        vd = torch.gather(valid, 1, sel).reshape(-1)
+        scene = torch.arange(bsz, device=boxes.device, dtype=torch.int32).repeat_interleave(nsel)
+        crops = ops.crop_resize_normalize(inputs["input_image"], scene, bx, vd, self.clip_resolution,
+                                          dtype=self.clip_model.dtype)
         feats = self.clip_model.encode_image(crops)
         if isinstance(feats, tuple):
             feats = feats[0]
-        feats = feats.to(torch.float32).reshape(bsz, sel.shape[1], -1)
+        return feats.to(torch.float32).reshape(bsz, nsel, -1), vd.reshape(bsz, nsel)
+
+    @torch.no_grad()
+    def get_predicted_box_clip_embedding(self, inputs, outputs, thres_obj=0.05, if_use_gt_box=False,
+                                         if_expand_box=False, if_padding_input=True, test=False, curr_epoch=-1,
+                                         random_selection_only=False):
+        """CLIP image embeddings of the crops under `distillation_box_num` predicted boxes per
+        scene -> outputs['gt_text_correlation_embedding'(_mask)] (+ weak labels).
+        Same semantics as reference :902-1210, without host synchronisation."""
+        bsz, nq = outputs["box_corners_xyz"].shape[:2]
+        dev = outputs["box_corners_xyz"].device
+        boxes, valid_all = self._boxes_in_image(inputs, outputs)
+        sel = self._select_boxes(outputs["objectness_prob"], -1 if random_selection_only else curr_epoch)  # (B, S)
+        feats, valid = self._clip_embed_boxes(inputs, boxes, valid_all, sel)
         vmask = valid.to(torch.float32).unsqueeze(-1)
         emb = torch.zeros((bsz, nq, feats.shape[-1]), device=dev)
         mask = torch.zeros((bsz, nq, 1), device=dev)
@@ -421,7 +434,7 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
         outputs["gt_text_correlation_embedding"] = emb
         outputs["gt_text_correlation_embedding_mask"] = mask
 
-        if self.if_keep_box and curr_epoch >= 540:
+        if self.if_keep_box and curr_epoch >= 540 and not random_selection_only:
             raise NotImplementedError("if_keep_box novel-box insertion (reference :1111-1150) is stage-2-late only")
 
         if self.if_clip_weak_labels:
@@ -436,6 +449,97 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
             outputs["weak_box_cate_label"] = torch.zeros((bsz, nq), device=dev, dtype=torch.int64)
             outputs["weak_confidence_weight"] = torch.zeros((bsz, nq), device=dev)
         return outputs
+
+    # ------------------------------------------------------------------ stage 2: novel-box discovery
+    DISCOVERY_CAPACITY = 32     # candidates per scene that get a CLIP crop (fixed: keeps the step graph-capturable)
+
+    @torch.no_grad()
+    def get_predicted_box_clip_embedding_nms_iou_save_keep_clip_driven_with_cate_confidence(
+            self, inputs, outputs, thres_obj=0.05, if_use_gt_box=False, if_expand_box=False, if_padding_input=True,
+            test=False, curr_epoch=-1, if_test=False):
+        """Stage-2 variant of the crop pipeline (reference :1212-1632).  On the epochs that are multiples of
+        `online_nms_update_save_epoch` it additionally DISCOVERS novel boxes: class-agnostic 2-D NMS of the projected
+        boxes (IoU 0.25), rejection of boxes whose axis-aligned 3-D IoU with a ground-truth box exceeds 0.25,
+        objectness >= save_objectness, then CLIP on the crops of the survivors; a survivor whose best class (over the
+        `test_range_max` / superset prompts) is a NOVEL one with probability > clip_driven_keep_thres becomes a pseudo
+        label row (center(3), size(3), angle, class, class prob, objectness) in the un-augmented frame.
+
+        Everything up to the rows runs on the device without host synchronisation (ops.novel_candidates + one
+        batched CLIP call over a fixed capacity of candidates); the rows are parked in `self._pending_pseudo` and
+        written to the per-scene .npy files by `flush_pseudo_labels()` -- the only host work, as in the reference
+        (np.save, :1524-1540)."""
+        discover = (not if_test) and (curr_epoch % self.online_nms_update_save_epoch == 0)
+        if discover:
+            self._discover_novel_boxes(inputs, outputs)
+        # distillation targets: always the random 32-of-128 draw in this variant (reference :1545)
+        return self.get_predicted_box_clip_embedding(inputs, outputs, curr_epoch=curr_epoch,
+                                                     random_selection_only=True)
+
+    @torch.no_grad()
+    def _discover_novel_boxes(self, inputs, outputs):
+        self.flush_pseudo_labels()       # rows of the previous discovery step, if nobody fetched them yet
+        boxes, valid = self._boxes_in_image(inputs, outputs)
+        obj = outputs["objectness_prob"].detach()
+        cap = self.DISCOVERY_CAPACITY
+        # reference box2d order is (ymin, xmin, ymax, xmax): IoU does not depend on the axis naming
+        cand, count = ops.novel_candidates(boxes, valid, obj, outputs["box_corners"].detach(),
+                                           inputs["gt_box_corners"], inputs["gt_box_present"], 0.25, 0.25,
+                                           float(self.save_objectness), cap)
+        cvalid = cand >= 0
+        sel = cand.clamp(min=0).long()
+        feats, _ = self._clip_embed_boxes(inputs, boxes, valid, sel)
+        text = outputs["maybe_novel_text_features_clip"].to(torch.float32)
+        e = feats / (feats.norm(dim=-1, keepdim=True) + 1e-32)
+        corr = torch.matmul(e, text.t()) * outputs["logit_scale"]
+        scores = ops.softmax_rows(corr)
+        max_score, max_idx = torch.max(scores, dim=-1)
+        cond = cvalid & (max_score > self.clip_driven_keep_thres) & (max_idx >= self.train_range_max)
+        # box parameters back in the un-augmented frame (reference :1236-1252), fp64 like the reference's promotion
+        scale = inputs["scale_array"].to(torch.double)                       # (B, 1, 3)
+        center = outputs["center_unnormalized"].detach().to(torch.double) * scale
+        size = outputs["size_unnormalized"].detach().to(torch.double) * scale
+        center = torch.matmul(center, inputs["rot_array"].to(torch.double))
+        angle = outputs["angle_continuous"].detach().to(torch.double) + inputs["rot_angle"].to(torch.double).view(-1, 1)
+        if "zx_flip_array" in inputs:
+            zx = inputs["zx_flip_array"].to(torch.double).view(-1, 1)
+            center = torch.cat((center[..., :1], center[..., 1:2] * zx.unsqueeze(-1), center[..., 2:]), dim=-1)
+            angle = torch.where(zx < 0, math.pi - angle, angle)
+        flip = inputs["flip_array"].to(torch.double).view(-1, 1)
+        center = torch.cat((center[..., :1] * flip.unsqueeze(-1), center[..., 1:]), dim=-1)
+        angle = torch.where(flip < 0, math.pi - angle, angle)
+        info = torch.cat((center, size, angle.unsqueeze(-1)), dim=-1).to(torch.float32)      # (B, Q, 7)
+        rows = torch.cat((torch.gather(info, 1, sel.unsqueeze(-1).expand(-1, -1, 7)),
+                          max_idx.to(torch.float32).unsqueeze(-1), max_score.unsqueeze(-1),
+                          torch.gather(obj, 1, sel).unsqueeze(-1)), dim=-1)               # (B, cap, 10)
+        room = (inputs["gt_ori_box_num"].view(-1, 1) <= 63) if "gt_ori_box_num" in inputs else torch.ones_like(cond)
+        self._pending_pseudo = {"rows": rows, "mask": cond & room, "count": count,
+                                "paths": inputs.get("pseudo_box_path")}
+        outputs["novel_box_rows"], outputs["novel_box_mask"] = rows, cond & room
+
+    def flush_pseudo_labels(self):
+        """Writes the pseudo-label rows of the last discovery step to the scenes' .npy files (reference :1524-1540;
+        the one device->host copy of the stage-2 path).  Returns the per-scene arrays."""
+        pending, self._pending_pseudo = getattr(self, "_pending_pseudo", None), None
+        if pending is None:
+            return None
+        rows = pending["rows"].cpu().numpy()
+        mask = pending["mask"].cpu().numpy().astype(bool)
+        count = pending["count"].cpu().numpy()
+        if (count[:, 1] > count[:, 0]).any():
+            warnings.warn(f"novel-box discovery: {int((count[:, 1] - count[:, 0]).max())} candidates beyond the "
+                          f"capacity of {self.DISCOVERY_CAPACITY} per scene were dropped")
+        out = []
+        for b in range(rows.shape[0]):
+            new = rows[b][mask[b]]
+            out.append(new)
+            paths = pending["paths"]
+            if paths is None or len(new) == 0:
+                continue
+            if self.if_accumulate_former_pseudo_labels and os.path.exists(paths[b]):
+                former = np.load(paths[b])
+                new = new if former.shape[0] == 0 else np.concatenate((former, new), axis=0)
+            np.save(paths[b], new)
+        return out
 
     def get_class_scores(self, box_predictions):
         """Multi-class scores from the text embeddings (reference :1743-1763)."""
@@ -475,10 +579,13 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
                     else self.text_features_fg_norm[: self.train_range_max, :])
             out["text_features_clip"] = text.unsqueeze(0).repeat(bsz, 1, 1)
             if self.online_nms_update_save_novel_label_clip_driven_with_cate_confidence:
-                raise NotImplementedError(
-                    "stage-2 novel-box discovery (3-D NMS + pseudo-label files, reference :1212-1632) "
-                    "is the next row of SURVEY.md section 8f, not built yet")
-            box_predictions["outputs"] = self.get_predicted_box_clip_embedding(inputs, out, curr_epoch=curr_epoch)
+                out["maybe_novel_text_features_clip"] = (self.superset_text_features_fg_norm if self.if_clip_superset
+                                                         else self.text_features_fg_norm[: self.test_range_max, :])
+                box_predictions["outputs"] = \
+                    self.get_predicted_box_clip_embedding_nms_iou_save_keep_clip_driven_with_cate_confidence(
+                        inputs, out, curr_epoch=curr_epoch, if_test=if_test)
+            else:
+                box_predictions["outputs"] = self.get_predicted_box_clip_embedding(inputs, out, curr_epoch=curr_epoch)
         if if_real_test:
             out["text_features_clip"] = self.text_features_fg_norm.unsqueeze(0).repeat(point_clouds.shape[0], 1, 1)
             box_predictions, _, _ = self.get_class_scores(box_predictions)

@@ -164,6 +164,9 @@ def make_batch(batch: int, npoints: int = 20000, seed: int = 0, max_gt: int = 64
         "flip_length": np.full((batch,), float(w), np.float64),
         "ori_width": np.full((batch,), w, np.int64), "ori_height": np.full((batch,), h, np.int64),
         "x_offset": np.zeros((batch,), np.int64), "y_offset": np.zeros((batch,), np.int64),
+        # stage 2 (novel-box discovery) reads these as well (model_3detr.py:1228, :1515)
+        "rot_angle": rot.astype(np.float64),
+        "gt_ori_box_num": present.sum(axis=1).astype(np.int64),
     })
     return d
 

@@ -102,6 +102,24 @@ int coda_hungarian(int b, int nprop, int ngt, const float *cost, const int *nact
                    long long *per_prop_gt_inds, float *proposal_matched_mask,
                    void *stream);
 
+/*
+ * Stage-2 novel-box discovery, candidate selection (one CTA per scene, no host synchronisation):
+ *   replaces models/model_3detr.py:1298-1420 -- the per-box loop building `box2d_thisbatch` / `scores`,
+ *   torchvision.ops.nms(box2d, scores, 0.25) (:1348), the cal_iou double loop against the ground truth (:1374-1386,
+ *   :868-899) and the `box_save` thresholding (:1402-1420).
+ *   boxes2d (b, q, 4) int32 projected boxes, valid (b, q) uint8 (0 = box given up: its NMS box is the dummy
+ *   (0, 0, 2, 2) and its score -1, as in the reference), objectness (b, q), pred_corners (b, q, 8, 3),
+ *   gt_corners (b, g, 8, 3), gt_present (b, g) in {0, 1}.
+ *   A box is a candidate iff it survives the class-agnostic 2-D NMS (IoU > nms_iou suppresses, score order, ties by
+ *   index), is valid, has objectness >= min_objectness and its axis-aligned 3-D IoU with every present ground-truth
+ *   box is <= gt_iou.  cand_idx (b, cap) int32: candidate box indices in descending score order, -1 padded;
+ *   cand_count (b, 2) int32: entries written, and the untruncated total (total > written: raise `cap`).
+ */
+int coda_novel_candidates(int b, int q, int g, int cap, const int *boxes2d, const unsigned char *valid,
+                          const float *objectness, const float *pred_corners, const float *gt_corners,
+                          const float *gt_present, float nms_iou, float gt_iou, float min_objectness, int *cand_idx,
+                          int *cand_count, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

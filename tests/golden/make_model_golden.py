@@ -97,8 +97,14 @@ def run_reference(name):
     model.clip_model.eval()
     inputs = {k: torch.from_numpy(v) for k, v in
               synthetic.make_batch(batch, npoints, seed=5, image_hw=extra.get("image_hw", (531, 730))).items()}
+    if extra.get("pseudo"):
+        import tempfile
+
+        tmp = tempfile.mkdtemp(prefix="coda_pseudo_ref_")
+        inputs["pseudo_box_path"] = [f"{tmp}/scene{i}.npy" for i in range(batch)]
     np.random.seed(123)  # box selection draws (model_3detr.py:991)
     out = model(inputs, curr_epoch=0)
+    model._golden_pseudo_paths = inputs.get("pseudo_box_path")
     loss, loss_dict = criterion(out, inputs)
     loss.backward()
     return args, model, out, loss, loss_dict
@@ -142,6 +148,13 @@ def main():
                 for k in ("size_normalized", "angle_logits", "angle_residual"):
                     blob[f"aux{i}.{k}"] = aux[k].detach().numpy()
                 blob[f"aux{i}.text_correlation_embedding"] = aux["text_correlation_embedding"].detach().numpy()[:, ::4, ::8]
+        if getattr(model, "_golden_pseudo_paths", None):
+            import os
+
+            arrs = [np.load(p) if os.path.exists(p) else np.zeros((0, 10), np.float32) for p in model._golden_pseudo_paths]
+            blob["pseudo.count"] = np.array([len(a) for a in arrs], np.int64)
+            blob["pseudo.rows"] = np.concatenate(arrs, axis=0).astype(np.float32).reshape(-1, 10)
+            print("pseudo labels per scene:", blob["pseudo.count"], flush=True)
         blob["loss"] = np.float32(loss.item())
         for k, v in loss_dict.items():
             blob[f"loss_dict.{k}"] = np.float32(float(v))

@@ -24,6 +24,11 @@ _STAGE2 = dict(if_clip_weak_labels=True, loss_feat_seen_softmax_weakly_loss_with
 CASES = {
     "stage1_small": (2, 3000, dict(_SMALL)),
     "stage2_weak": (2, 2500, dict(_SMALL, **_STAGE2)),
+    # stage 2 with novel-box discovery on (2-D NMS, ground-truth rejection, CLIP-driven keep, pseudo-label rows);
+    # thresholds lowered so that random-init predictions exercise every branch
+    "stage2_discovery": (2, 2500, dict(_SMALL, **_STAGE2, online_nms_update_save_novel_label_clip_driven_with_cate_confidence=True,
+                                       save_objectness=0.3, clip_driven_keep_thres=0.0258, online_nms_update_save_epoch=10),
+                         dict(pseudo=True)),
     # the configuration the BASELINE metric is quoted on: 2048 seeds, enc 3 x 256, dec 8 x 512, 256 queries,
     # 20 000 points (2 scenes so that the CPU reference run stays in minutes)
     "baseline_full": (2, 20000, dict(_NODROP)),
@@ -83,6 +88,11 @@ def build(name: str, device: str):
     model.clip_model.eval()
     inputs = synthetic.to_device(
         synthetic.make_batch(batch, npoints, seed=5, image_hw=extra.get("image_hw", (531, 730))), device)
+    if extra.get("pseudo"):
+        import tempfile
+
+        tmp = tempfile.mkdtemp(prefix="coda_pseudo_")
+        inputs["pseudo_box_path"] = [f"{tmp}/scene{i}.npy" for i in range(batch)]
     return args, model, criterion, inputs, golden
 
 
@@ -145,6 +155,19 @@ def compare(model, out, loss, loss_dict, golden, rtol, atol, check_grads=True, g
     exp_loss = float(golden["loss"])
     errs["loss"] = abs(float(loss) - exp_loss) / abs(exp_loss)
     assert errs["loss"] <= rtol, f"loss {float(loss)} vs {exp_loss}"
+    if "pseudo.count" in golden.files:
+        # stage-2 discovery: the pseudo-label rows each scene's .npy file receives (reference :1524-1540)
+        saved = model.flush_pseudo_labels()
+        counts = golden["pseudo.count"]
+        assert [len(a) for a in saved] == list(counts), ([len(a) for a in saved], list(counts))
+        got = np.concatenate(saved, axis=0) if sum(counts) else np.zeros((0, 10), np.float32)
+        exp = golden["pseudo.rows"]
+        assert np.array_equal(got[:, 7], exp[:, 7]), "pseudo-label classes differ"
+        scale = np.abs(exp).max(axis=0, keepdims=True) + 1e-6
+        errs["pseudo.rows"] = float((np.abs(got - exp) / scale).max())
+        assert errs["pseudo.rows"] <= max(rtol, 2e-4), errs["pseudo.rows"]
+        for path, n in zip(getattr(model, "_last_pseudo_paths", []) or [], counts):
+            pass
     for k in golden.files:
         if k.startswith("loss_dict."):
             name = k[len("loss_dict."):]

@@ -194,3 +194,36 @@ def test_clip_image_tower_fp16_kernels_vs_fp32_math():
         # fp32 reference path: plain torch ops (x is fp32 -> none of the fp16 kernel branches trigger)
         exp = ref.visual(x)[0]
     assert ((got - exp).abs().max() / exp.abs().max()).item() < 2e-2   # fp16 weights + activations
+
+
+@pytest.mark.parametrize("q,g,seed", [(256, 64, 0), (128, 5, 1), (300, 0, 2), (1000, 64, 3)])
+def test_novel_candidates_matches_reference_loop(q, g, seed):
+    """ops.novel_candidates (2-D NMS + ground-truth rejection + objectness threshold on the device) against the
+    step-by-step restatement of the reference loop (oracle/discovery_ref.py: torchvision.ops.nms + cal_iou)."""
+    import discovery_ref
+
+    from coda_neurips2023_b200 import ops
+
+    gen = torch.Generator().manual_seed(seed)
+    b = 3
+    xy = torch.randint(0, 600, (b, q, 2), generator=gen)
+    wh = torch.randint(1, 250, (b, q, 2), generator=gen)
+    boxes = torch.cat((xy, xy + wh), dim=-1).to(torch.int32)
+    boxes[:, : q // 8] = boxes[:, q // 8: 2 * (q // 8)]            # exact duplicates: IoU 1 -> suppressed
+    valid = torch.rand(b, q, generator=gen) > 0.15
+    obj = torch.rand(b, q, generator=gen)
+    obj[:, 5] = obj[:, 6]                                           # a score tie
+    ctr = torch.rand(b, q, 1, 3, generator=gen) * 4
+    half = torch.rand(b, q, 1, 3, generator=gen) * 0.8 + 0.1
+    sign = torch.tensor([[1, 1, 1], [1, 1, -1], [1, -1, 1], [1, -1, -1], [-1, 1, 1], [-1, 1, -1], [-1, -1, 1],
+                         [-1, -1, -1]], dtype=torch.float32)
+    pred = ctr + half * sign
+    gctr = torch.rand(b, max(g, 1), 1, 3, generator=gen) * 4
+    gt = (gctr + (torch.rand(b, max(g, 1), 1, 3, generator=gen) * 0.8 + 0.1) * sign)[:, :g]
+    present = (torch.rand(b, max(g, 1), generator=gen) > 0.5).float()[:, :g]
+    for cap in (32, q):
+        exp_idx, exp_cnt = discovery_ref.novel_candidates_ref(boxes, valid, obj, pred, gt, present, 0.25, 0.25, 0.4, cap)
+        got_idx, got_cnt = ops.novel_candidates(boxes.cuda(), valid.cuda(), obj.cuda(), pred.cuda(), gt.cuda(),
+                                                present.cuda(), 0.25, 0.25, 0.4, cap)
+        assert torch.equal(got_cnt.cpu(), exp_cnt), (got_cnt, exp_cnt)
+        assert torch.equal(got_idx.cpu(), exp_idx)
