@@ -441,14 +441,15 @@ int launch_a32(const A32Maps &maps, const A32Params &P, cudaStream_t s) {
   static_assert(RAW_KB % 64 == 0 || RAW_KB == 96, "raw region");
   constexpr size_t smem = (size_t)RAW_KB * 1024 + (size_t)B_STAGES * NSPLIT * BN * BK * 2 + 4 * 32 * 128 + 1024;
   const size_t total = smem + (P.stats ? (size_t)8 * P.n * 4 : 0);
-  if (total > 227 * 1024) return CODA_ETOOLARGE;
+  constexpr size_t SMEM_MAX = 227 * 1024 - 2048;     // static shared memory (barriers) shares the 227 KB limit
+  if (total > SMEM_MAX) return CODA_ETOOLARGE;
   if (P.mode == CODA_A32_BN_BWD && RAW_KB < 64) return CODA_EINVAL;
   auto kern = gemm_a32_kernel<NSPLIT, BN, RAW_KB, B_STAGES, B_MN>;
   static size_t configured = 0;
   if (configured < total) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
     if (e != cudaSuccess) return (int)e;
-    configured = 227 * 1024;
+    configured = SMEM_MAX;
   }
   const long long nwork = (long long)((P.m + BM - 1) / BM) * ((P.n + BN - 1) / BN);
   const unsigned grid = (unsigned)(nwork < num_sms() ? nwork : num_sms());

@@ -16,6 +16,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline EncodeTiledFn encode_tiled_fn() {
+  // cuTensorMapEncodeTiled validates the global address against the CURRENT context.  An entry point that encodes a
+  // map before its first runtime call can be the first CUDA call of its thread (autograd's backward worker): bind the
+  // primary context to the thread once.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void *p = nullptr;

@@ -70,6 +70,8 @@ class FlatParameters:
     """Re-homes every trainable parameter of `module` (and its gradient) into one contiguous fp32 buffer each.
     `order` (a permutation of the trainable parameters) fixes the layout; default = registration order."""
 
+    ALIGN = 64   # elements
+
     def __init__(self, module: torch.nn.Module, order=None):
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
         params = [p for _, p in named] if order is None else list(order)
@@ -77,8 +79,11 @@ class FlatParameters:
         assert {id(p) for p in params} == {id(p) for _, p in named}, "order must be a permutation of the parameters"
         name_of = {id(p): n for n, p in named}
         dev = params[0].device
-        total = sum(p.numel() for p in params)
-        self.flat_param = torch.nn.Parameter(torch.empty(total, dtype=torch.float32, device=dev))
+        # every parameter starts on a 256-byte boundary: kernels read per-channel vectors (BatchNorm / LayerNorm
+        # scales, biases) with 16-byte loads and TMA addresses weight rows; the few padding elements stay zero
+        pad = lambda n: (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN  # noqa: E731
+        total = sum(pad(p.numel()) for p in params)
+        self.flat_param = torch.nn.Parameter(torch.zeros(total, dtype=torch.float32, device=dev))
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.offsets, self.names = [], []
         off = 0
@@ -90,7 +95,7 @@ class FlatParameters:
                 p.grad = self.flat_grad[off:off + n].view_as(p)
                 self.offsets.append(off)
                 self.names.append(name_of[id(p)])
-                off += n
+                off += pad(n)
         self.flat_param.grad = self.flat_grad
         self.params = params
 

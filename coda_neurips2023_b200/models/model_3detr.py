@@ -374,16 +374,28 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
                          for _ in range(bsz)]).astype(np.int64)
 
     def _select_boxes(self, objectness_prob, curr_epoch):
-        """(B, distillation_box_num) box indices per scene.  Stage 1 (and < epoch 540):
-        `np.random.choice(arange(128), 32, replace=False)` per scene on the host RNG,
-        exactly the reference's draw sequence (:991)."""
-        bsz = objectness_prob.shape[0]
+        """(sel (B, S) box indices, chosen (B, S) bool).  Stage 1 (and < epoch 540): S = distillation_box_num,
+        `np.random.choice(arange(128), 32, replace=False)` per scene on the host RNG, exactly the reference's draw
+        sequence (:991), all chosen.  With `if_select_box_by_objectness` from epoch 540 on (reference :993-1004): every
+        box with objectness > 0.05, topped up to distillation_box_num with randomly drawn background boxes when there
+        are fewer -- here S = nqueries with a mask, so the crop batch keeps a static shape.  The top-up draw uses the
+        device RNG (the reference draws it from numpy on host-copied indices: a host sync per scene)."""
+        bsz, nq = objectness_prob.shape
+        dev = objectness_prob.device
         if (not self.if_select_box_by_objectness) or curr_epoch < 540:
             if self.external_selection is not None:   # drawn ahead of the (graph-captured) step
-                return self.external_selection
-            return torch.from_numpy(self.draw_box_selection(bsz)).to(objectness_prob.device, non_blocking=True)
-        raise NotImplementedError("objectness-driven crop selection after epoch 540 (reference :993-1006) yields a "
-                                  "variable number of crops per scene; not on the B200 path yet")
+                sel = self.external_selection
+            else:
+                sel = torch.from_numpy(self.draw_box_selection(bsz)).to(dev, non_blocking=True)
+            return sel, torch.ones_like(sel, dtype=torch.bool)
+        is_obj = objectness_prob > 0.05
+        n_obj = is_obj.sum(dim=1, keepdim=True)
+        # background boxes in random order; the first (distillation_box_num - n_obj) of them are drawn
+        prio = torch.rand((bsz, nq), device=dev).masked_fill(is_obj, 2.0)
+        rank_bg = prio.argsort(dim=1).argsort(dim=1)                   # 0 .. n_bg-1 among background boxes
+        fill = (~is_obj) & (rank_bg < (self.distillation_box_num - n_obj))
+        sel = torch.arange(nq, device=dev).unsqueeze(0).expand(bsz, -1)
+        return sel, is_obj | fill
 
     @torch.no_grad()
     def _boxes_in_image(self, inputs, outputs):
@@ -401,11 +413,14 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
         return torch.stack((xmin, ymin, xmax, ymax), dim=-1), valid
 
     @torch.no_grad()
-    def _clip_embed_boxes(self, inputs, boxes, valid, sel):
+    def _clip_embed_boxes(self, inputs, boxes, valid, sel, chosen=None):
         """CLIP image embeddings of the crops under boxes[b, sel[b, s]] -> (B, S, D) fp32 (garbage where invalid)."""
         bsz, nsel = sel.shape
         bx = torch.gather(boxes, 1, sel.unsqueeze(-1).expand(-1, -1, 4)).reshape(-1, 4).contiguous()
-        vd = torch.gather(valid, 1, sel).reshape(-1)
+        vd = torch.gather(valid, 1, sel)
+        if chosen is not None:
+            vd = vd & chosen
+        vd = vd.reshape(-1)
         scene = torch.arange(bsz, device=boxes.device, dtype=torch.int32).repeat_interleave(nsel)
         crops = ops.crop_resize_normalize(inputs["input_image"], scene, bx, vd, self.clip_resolution,
                                           dtype=self.clip_model.dtype)
@@ -424,8 +439,9 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
         bsz, nq = outputs["box_corners_xyz"].shape[:2]
         dev = outputs["box_corners_xyz"].device
         boxes, valid_all = self._boxes_in_image(inputs, outputs)
-        sel = self._select_boxes(outputs["objectness_prob"], -1 if random_selection_only else curr_epoch)  # (B, S)
-        feats, valid = self._clip_embed_boxes(inputs, boxes, valid_all, sel)
+        sel, chosen = self._select_boxes(outputs["objectness_prob"].detach(),
+                                         -1 if random_selection_only else curr_epoch)      # (B, S)
+        feats, valid = self._clip_embed_boxes(inputs, boxes, valid_all, sel, chosen)
         vmask = valid.to(torch.float32).unsqueeze(-1)
         emb = torch.zeros((bsz, nq, feats.shape[-1]), device=dev)
         mask = torch.zeros((bsz, nq, 1), device=dev)
@@ -435,7 +451,7 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
         outputs["gt_text_correlation_embedding_mask"] = mask
 
         if self.if_keep_box and curr_epoch >= 540 and not random_selection_only:
-            raise NotImplementedError("if_keep_box novel-box insertion (reference :1111-1150) is stage-2-late only")
+            self._keep_novel_boxes_as_gt(inputs, outputs, sel, valid, feats)
 
         if self.if_clip_weak_labels:
             text = outputs["text_features_clip"].to(torch.float32)
@@ -449,6 +465,47 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
             outputs["weak_box_cate_label"] = torch.zeros((bsz, nq), device=dev, dtype=torch.int64)
             outputs["weak_confidence_weight"] = torch.zeros((bsz, nq), device=dev)
         return outputs
+
+    @torch.no_grad()
+    def _keep_novel_boxes_as_gt(self, inputs, outputs, sel, valid, feats):
+        """`if_keep_box` from epoch 540 on (reference :1106-1150): a selected, croppable box with objectness >
+        keep_objectness whose CLIP class over the training prompts is novel (probability > 0.5, class id > 9) is
+        APPENDED to the scene's ground truth (slots gt_box_present.sum() .. 63, in selection order) with the model's
+        own prediction as the label.  Mutates `inputs` in place like the reference; tensor ops only, no host sync."""
+        obj = torch.gather(outputs["objectness_prob"].detach(), 1, sel)
+        text = outputs["text_features_clip"].to(torch.float32)
+        e = feats / (feats.norm(dim=-1, keepdim=True) + 1e-32)
+        scores = ops.softmax_rows(torch.bmm(e, text.permute(0, 2, 1)) * outputs["logit_scale"])
+        max_score, max_id = torch.max(scores, dim=-1)
+        novel = valid & (obj > self.keep_objectness) & (max_score > 0.5) & (max_id > 9)        # (B, S), selection order
+        begin = inputs["gt_box_present"].sum(dim=1).long().view(-1, 1)
+        dest = begin + torch.cumsum(novel.long(), dim=1) - 1
+        ngt = inputs["gt_box_present"].shape[1]
+        ok = novel & (dest < ngt)                      # `begin_idx > 63 -> break`
+        dest = torch.where(ok, dest, torch.full_like(dest, ngt))      # rejected entries go to a scratch slot
+
+        def put(key, values):
+            """inputs[key][b, dest[b, s]] = values[b, s] for the accepted (b, s)"""
+            tgt = inputs[key]
+            vals = values.to(tgt.dtype)
+            pad = torch.cat((tgt, tgt.new_zeros((tgt.shape[0], 1) + tuple(tgt.shape[2:]))), dim=1)
+            idx = dest.view(dest.shape + (1,) * (tgt.dim() - 2)).expand(-1, -1, *tgt.shape[2:])
+            pad.scatter_(1, idx, vals)
+            tgt.copy_(pad[:, :ngt])
+
+        take = lambda t: torch.gather(t.detach(), 1, sel.view(sel.shape + (1,) * (t.dim() - 2)).expand(-1, -1, *t.shape[2:]))  # noqa: E731
+        angle_cls = take(outputs["angle_logits"]).softmax(dim=-1).argmax(dim=-1)
+        put("gt_box_present", torch.ones_like(dest))
+        put("gt_angle_class_label", angle_cls)
+        put("gt_angle_residual_label", torch.gather(take(outputs["angle_residual"]), 2, angle_cls.unsqueeze(-1)).squeeze(-1))
+        put("gt_box_sizes_normalized", take(outputs["size_normalized"]))
+        put("gt_box_sizes", take(outputs["size_unnormalized"]))
+        put("gt_box_corners", take(outputs["box_corners"]))
+        if "gt_box_corners_xyz" in inputs:
+            put("gt_box_corners_xyz", take(outputs["box_corners_xyz"]))
+        put("gt_box_angles", take(outputs["angle_continuous"]))
+        put("gt_box_centers_normalized", take(outputs["center_normalized"]))
+        put("gt_box_centers", take(outputs["center_unnormalized"]))
 
     # ------------------------------------------------------------------ stage 2: novel-box discovery
     DISCOVERY_CAPACITY = 32     # candidates per scene that get a CLIP crop (fixed: keeps the step graph-capturable)

@@ -103,7 +103,7 @@ def run_reference(name):
         tmp = tempfile.mkdtemp(prefix="coda_pseudo_ref_")
         inputs["pseudo_box_path"] = [f"{tmp}/scene{i}.npy" for i in range(batch)]
     np.random.seed(123)  # box selection draws (model_3detr.py:991)
-    out = model(inputs, curr_epoch=0)
+    out = model(inputs, curr_epoch=extra.get("curr_epoch", 0))
     model._golden_pseudo_paths = inputs.get("pseudo_box_path")
     loss, loss_dict = criterion(out, inputs)
     loss.backward()

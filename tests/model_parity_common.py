@@ -29,6 +29,9 @@ CASES = {
     "stage2_discovery": (2, 2500, dict(_SMALL, **_STAGE2, online_nms_update_save_novel_label_clip_driven_with_cate_confidence=True,
                                        save_objectness=0.3, clip_driven_keep_thres=0.0258, online_nms_update_save_epoch=10),
                          dict(pseudo=True)),
+    # stage 2 late: objectness-driven crop selection (every box with objectness > 0.05) + if_keep_box, epoch >= 540
+    "stage2_late": (2, 2500, dict(_SMALL, **_STAGE2, if_select_box_by_objectness=True, if_keep_box=True),
+                    dict(curr_epoch=540)),
     # the configuration the BASELINE metric is quoted on: 2048 seeds, enc 3 x 256, dec 8 x 512, 256 queries,
     # 20 000 points (2 scenes so that the CPU reference run stays in minutes)
     "baseline_full": (2, 20000, dict(_NODROP)),
@@ -99,7 +102,7 @@ def build(name: str, device: str):
 def run(name: str, device: str):
     args, model, criterion, inputs, golden = build(name, device)
     np.random.seed(123)
-    out = model(inputs, curr_epoch=0)
+    out = model(inputs, curr_epoch=case(name)[3].get("curr_epoch", 0))
     loss, loss_dict = criterion(out, inputs)
     loss.backward()
     return model, out, loss, loss_dict, golden
@@ -115,11 +118,11 @@ def cpu_noise(name: str) -> dict:
 
 def compare(model, out, loss, loss_dict, golden, rtol, atol, check_grads=True, grad_rtol=None, noise=None):
     """Returns a dict name -> max relative error; raises on the first mismatch.  `noise` (cpu_noise) widens a
-    gradient's bar to 3 x the deviation another fp32 implementation shows on the same key."""
+    gradient's bar to 4 x the deviation another fp32 implementation shows on the same key."""
     errs = {}
     noise = noise or {}
 
-    def chk(key, got, sl=None, rtol=rtol):
+    def chk(key, got, sl=None, rtol=rtol, atol=atol):
         exp = golden[key]
         g = got.detach().float().cpu().numpy()
         if sl is not None:
@@ -184,5 +187,6 @@ def compare(model, out, loss, loss_dict, golden, rtol, atol, check_grads=True, g
             if k.startswith("grad."):
                 # gradients cross ~13 layers and train-mode BatchNorm: looser than the forward bar
                 gr = grad_rtol if grad_rtol is not None else 10 * rtol
-                chk(k, params[k[len("grad."):]].grad, rtol=max(gr, 3.0 * noise.get(k, 0.0)))
+                # a gradient tensor whose entries are all tiny is held to an absolute bar as well (1e-4)
+                chk(k, params[k[len("grad."):]].grad, rtol=max(gr, 4.0 * noise.get(k, 0.0)), atol=1e-4)
     return errs

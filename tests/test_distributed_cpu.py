@@ -42,7 +42,8 @@ def _worker(rank, world, port, ret):
     gathered = cdist.all_gather_dict({"x": torch.full((2, 3), float(rank))})
     cdist.barrier()
     if rank == 0:
-        ret["flat_grad"] = flat.flat_grad.clone()
+        # the flat buffer pads every parameter to a 256-byte boundary: compare the parameters' own slices
+        ret["flat_grad"] = torch.cat([p.grad.reshape(-1) for p in flat.params]).clone()
         ret["total"], ret["avg"] = total.item(), avg.item()
         ret["red"] = {k: v.item() for k, v in red.items()}
         ret["gathered"] = gathered["x"].clone()
