@@ -108,8 +108,12 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char *raw_ring = smem;
   const bool two_in = P.mode == CODA_A32_BN_BWD;
-  const int raw_stage_bytes = RAW_TILE * (two_in ? 2 : 1);
-  const uint32_t nraw = two_in ? (uint32_t)(MAX_RAW / 2) : (uint32_t)MAX_RAW;
+  const bool pooled = P.mode == CODA_A32_BN_BWD_POOLED;
+  // pooled BatchNorm backward: each raw stage carries, after the fp32 tile, the (group, channel) gradient and
+  // arg-max rows of the tile's groups for this k-block: [groups in tile][64 floats | 64 bytes]  (<= 1 KB)
+  const int raw_stage_bytes = RAW_TILE * (two_in ? 2 : 1) + (pooled ? 1024 : 0);
+  const uint32_t nraw = (uint32_t)((RAW_KB * 1024) / raw_stage_bytes);
+  const int tile_groups = pooled ? (P.group >= BM ? 1 : BM / P.group) : 0;
   unsigned char *b_ring = smem + (size_t)RAW_KB * 1024;
   unsigned char *epi = b_ring + (size_t)B_STAGES * B_STAGE;                // 4 x [32 x 128 B] staging tiles
   float *s_stats = reinterpret_cast<float *>(epi + 4 * 32 * 128);          // [4 warps][2][n]  (only if P.stats)
@@ -167,7 +171,16 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
         mbar_wait(&b_empty[bs], ((it / B_STAGES) & 1u) ^ 1u);
         if (elect_one_sync()) {
           unsigned char *rt = raw_ring + (size_t)rs * raw_stage_bytes;
-          mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)raw_stage_bytes);
+          mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)(RAW_TILE * (two_in ? 2 : 1) + tile_groups * 320));
+          if (pooled) {
+            const long long ngroups = P.m / P.group;
+            for (int gt = 0; gt < tile_groups; ++gt) {
+              long long g = (long long)m0 / P.group + gt;
+              if (g >= ngroups) g = ngroups - 1;        // rows past m: values unused
+              bulk_load_1d(rt + RAW_TILE + gt * 320, P.dpooled + g * P.k + kb * BK, 256, &raw_full[rs]);
+              bulk_load_1d(rt + RAW_TILE + gt * 320 + 256, P.argmax + g * P.k + kb * BK, 64, &raw_full[rs]);
+            }
+          }
           tma_load_3d(rt, &maps.a, &raw_full[rs], kb * BK, m0, 0);
           tma_load_3d(rt + RAW_TILE / 2, &maps.a, &raw_full[rs], kb * BK + 32, m0, 0);
           if (two_in) {
@@ -235,6 +248,11 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
       int m0, n0;
       decode(w, m0, n0);
       const long long grow = (long long)m0 + row;     // global row (mode 3: its group / index within the group)
+      int pgt = 0, pgi = 0;       // pooled mode: this row's group within the tile, its index within the group
+      if (pooled) {
+        pgi = (int)(grow % P.group);
+        pgt = P.group >= BM ? 0 : row / P.group;
+      }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int rs = it % nraw, as = it % A_STAGES;
         mbar_wait(&raw_full[rs], (it / nraw) & 1u);
@@ -285,21 +303,16 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
           } else if (P.mode == CODA_A32_BN_BWD_POOLED) {
             // the layer output was max-pooled over `group` rows: only the arg-max row of a (group, channel)
             // carries the incoming gradient dpooled[g][c]
-            const long long g = grow / P.group;
-            const int gi = (int)(grow - g * P.group);
-            const bool live = grow < P.m;
+            const int gi = pgi;
+            const unsigned char *px = rt + RAW_TILE + pgt * 320;     // staged by the producer with the raw tile
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 s4 = __ldg(reinterpret_cast<const float4 *>(P.scale + kc) + j);
               const float4 t4 = __ldg(reinterpret_cast<const float4 *>(P.shift + kc) + j);
               const float4 a4 = __ldg(reinterpret_cast<const float4 *>(P.alpha + kc) + j);
               const float4 b4 = __ldg(reinterpret_cast<const float4 *>(P.beta + kc) + j);
-              float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-              uchar4 id = make_uchar4(255, 255, 255, 255);
-              if (live && kc + 4 * j < P.k) {
-                d = __ldg(reinterpret_cast<const float4 *>(P.dpooled + g * P.k + kc) + j);
-                id = __ldg(reinterpret_cast<const uchar4 *>(P.argmax + g * P.k + kc) + j);
-              }
+              const float4 d = *reinterpret_cast<const float4 *>(px + (ch * 16 + 4 * j) * 4);
+              const uchar4 id = *reinterpret_cast<const uchar4 *>(px + 256 + ch * 16 + 4 * j);
               x[4 * j] = ((id.x == gi && fmaf(x[4 * j], s4.x, t4.x) > 0.f) ? s4.x * d.x : 0.f) + fmaf(x[4 * j], a4.x, b4.x);
               x[4 * j + 1] = ((id.y == gi && fmaf(x[4 * j + 1], s4.y, t4.y) > 0.f) ? s4.y * d.y : 0.f) + fmaf(x[4 * j + 1], a4.y, b4.y);
               x[4 * j + 2] = ((id.z == gi && fmaf(x[4 * j + 2], s4.z, t4.z) > 0.f) ? s4.z * d.z : 0.f) + fmaf(x[4 * j + 2], a4.z, b4.z);
@@ -481,7 +494,10 @@ int coda_gemm_a32(int nsplit, int m, int n, int k, const float *a, long long lda
   if (a_mode != CODA_A32_PLAIN && (!a_scale || !a_shift || (k & 3))) return CODA_EINVAL;
   if (a_mode >= CODA_A32_BN_BWD && (!a2 || !a_alpha || !a_beta || ((uintptr_t)a2 & 15))) return CODA_EINVAL;
   if (a_mode == CODA_A32_BN_BWD && (lda2 & 3)) return CODA_EINVAL;
-  if (a_mode == CODA_A32_BN_BWD_POOLED && (!a_argmax || a_group < 1 || a_group > 256 || m % a_group != 0)) return CODA_EINVAL;
+  if (a_mode == CODA_A32_BN_BWD_POOLED &&
+      (!a_argmax || a_group < 32 || a_group > 256 || m % a_group != 0 || k % 64 != 0 ||
+       !(a_group % 128 == 0 || 128 % a_group == 0) || a_group % 32 != 0))
+    return CODA_EINVAL;     // groups must tile the 128-row blocks (warp = 32 rows of one group)
   const int bn = n <= 64 ? 64 : 128;
   A32Maps maps;
   int st = make_tmap_f32_box(&maps.a, a, k, m, lda, 32, BM);
@@ -514,12 +530,15 @@ int coda_gemm_a32(int nsplit, int m, int n, int k, const float *a, long long lda
   cudaStream_t s = (cudaStream_t)stream;
 #define CODA_A32(NS, BN_, RS, BS)                                                   \
   return b_mn ? launch_a32<NS, BN_, RS, BS, true>(maps, P, s) : launch_a32<NS, BN_, RS, BS, false>(maps, P, s)
-  // smem: raw region + B ring + 16 KB staging (+ stats): <= 227 KB
+  // smem: raw region + B ring + 16 KB staging (+ stats): <= 225 KB.  The B (weight) tiles come from L2 with ~1 us
+  // latency: long contractions want a deep B ring, the two-input prologue a wide raw region.
+  const bool deep_b = !col_stats && k > 128 && a_mode != CODA_A32_BN_BWD;
   if (nsplit == 2) {
     if (bn == 64) CODA_A32(2, 64, 128, 4);
     CODA_A32(2, 128, 128, 2);
   }
   if (bn == 64) CODA_A32(3, 64, 128, 3);
+  if (deep_b) CODA_A32(3, 128, 64, 3);
   CODA_A32(3, 128, 96, 2);
 #undef CODA_A32
 }

@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(512, 1)
 gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
   constexpr int RAW_A = BKR * BM * 4;            // 16 KB: four [32 rows x 32 fp32] SW128 boxes
   constexpr int RAW_B = BKR * BN * 4;
-  constexpr int RAW_STAGE = 2 * RAW_A + RAW_B;   // (second A input present only in the dense BN-backward mode)
+  constexpr int RAW_X = 1024;                    // pooled mode: [128 floats dpooled | 128 bytes argmax] of the slab's group
+  constexpr int RAW_STAGE = 2 * RAW_A + RAW_B + RAW_X;   // (second A input only in the dense BN-backward mode)
   constexpr int PL_A = BKR * BM * 2;             // one bf16 plane of the A slab: two [32 x 64] boxes
   constexpr int PL_B = BKR * BN * 2;
   constexpr int PL_STAGE = NS * (PL_A + PL_B);
@@ -123,7 +124,9 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
 
   if (warp == 0) {
     // ===== TMA producer =====
-    const uint32_t bytes = (uint32_t)(RAW_A * (two_in ? 2 : 1) + RAW_B);
+    const bool pooled = P.a_mode == CODA_A32_BN_BWD_POOLED;
+    const uint32_t bytes = (uint32_t)(RAW_A * (two_in ? 2 : 1) + RAW_B + (pooled ? 640 : 0));
+    const long long ngroups = pooled ? P.rows / P.group : 0;
     for (long long i = 0; i < nkb; ++i) {
       const int rs = (int)(i % RAW_STAGES);
       mbar_wait(&raw_empty[rs], (uint32_t)((i / RAW_STAGES) & 1) ^ 1u);
@@ -131,6 +134,13 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
         unsigned char *st = raw_ring + (size_t)rs * RAW_STAGE;
         const int r0 = (int)((kb0 + i) * BKR);
         mbar_arrive_expect_tx(&raw_full[rs], bytes);
+        if (pooled) {      // the slab (32 rows) lies in one group (group % 32 == 0)
+          long long g = (long long)r0 / P.group;
+          if (g >= ngroups) g = ngroups - 1;
+          // m0 + 128 <= padded m: the host guarantees m % 128 == 0 in this mode
+          bulk_load_1d(st + 2 * RAW_A + RAW_B, P.dpooled + g * P.m + m0, 512, &raw_full[rs]);
+          bulk_load_1d(st + 2 * RAW_A + RAW_B + 512, P.argmax + g * P.m + m0, 128, &raw_full[rs]);
+        }
 #pragma unroll
         for (int g = 0; g < BM / 32; ++g) tma_load_3d(st + g * 4096, &maps.a, &raw_full[rs], m0 + g * 32, r0, 0);
         if (two_in) {
@@ -196,6 +206,8 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
       const unsigned char *raw = raw_ring + (size_t)rs * RAW_STAGE;
       unsigned char *pl = pl_ring + (size_t)ps * PL_STAGE;
       const long long r0 = (kb0 + i) * BKR;
+      int rem0 = 0;
+      if (P.a_mode == CODA_A32_BN_BWD_POOLED) rem0 = (int)(r0 % P.group);    // the slab's first row within its group
       // ---- A slab
 #pragma unroll
       for (int j = 0; j < BKR / 8; ++j) {
@@ -211,14 +223,9 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
           o.z = (fmaf(y.z, sa.z, ta.z) > 0.f ? sa.z * d.z : 0.f) + fmaf(y.z, al.z, be.z);
           o.w = (fmaf(y.w, sa.w, ta.w) > 0.f ? sa.w * d.w : 0.f) + fmaf(y.w, al.w, be.w);
         } else if (P.a_mode == CODA_A32_BN_BWD_POOLED) {
-          float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-          uchar4 id = make_uchar4(255, 255, 255, 255);
-          const long long g = grow / P.group;
-          const int gi = (int)(grow - g * P.group);
-          if (grow < P.rows && a_col_ok) {
-            d = __ldg(reinterpret_cast<const float4 *>(P.dpooled + g * P.m + ca));
-            id = __ldg(reinterpret_cast<const uchar4 *>(P.argmax + g * P.m + ca));
-          }
+          const int gi = rem0 + r;
+          const float4 d = *reinterpret_cast<const float4 *>(raw + 2 * RAW_A + RAW_B + lane * 16);
+          const uchar4 id = *reinterpret_cast<const uchar4 *>(raw + 2 * RAW_A + RAW_B + 512 + lane * 4);
           o.x = ((id.x == gi && fmaf(y.x, sa.x, ta.x) > 0.f) ? sa.x * d.x : 0.f) + fmaf(y.x, al.x, be.x);
           o.y = ((id.y == gi && fmaf(y.y, sa.y, ta.y) > 0.f) ? sa.y * d.y : 0.f) + fmaf(y.y, al.y, be.y);
           o.z = ((id.z == gi && fmaf(y.z, sa.z, ta.z) > 0.f) ? sa.z * d.z : 0.f) + fmaf(y.z, al.z, be.z);
@@ -306,7 +313,7 @@ inline int make_tmap_f32_box(CUtensorMap *map, const void *base, long long cols,
 
 template <int BN>
 int launch_tn32(const TN32Maps &maps, TN32Params P, float *c, long long ldc, cudaStream_t s) {
-  constexpr size_t smem = (size_t)RAW_STAGES * (2 * BKR * BM * 4 + BKR * BN * 4) +
+  constexpr size_t smem = (size_t)RAW_STAGES * (2 * BKR * BM * 4 + BKR * BN * 4 + 1024) +
                           (size_t)PL_STAGES * NS * (BKR * BM * 2 + BKR * BN * 2) + 4 * 32 * 128 + 1024;
   static_assert(smem <= 227 * 1024, "smem budget");
   auto kern = gemm_tn32_kernel<BN>;
@@ -352,7 +359,9 @@ int coda_gemm_tn32(long long rows, int m, int n, const float *a, long long lda, 
   if (b_mode != CODA_A32_PLAIN && b_mode != CODA_A32_AFFINE_RELU) return CODA_EINVAL;
   if (a_mode != CODA_A32_PLAIN && (!a_scale || !a_shift || !a_alpha || !a_beta || !a2 || ((uintptr_t)a2 & 15))) return CODA_EINVAL;
   if (a_mode == CODA_A32_BN_BWD && (lda2 & 3)) return CODA_EINVAL;
-  if (a_mode == CODA_A32_BN_BWD_POOLED && (!a_argmax || a_group < 1 || a_group > 256 || rows % a_group != 0)) return CODA_EINVAL;
+  if (a_mode == CODA_A32_BN_BWD_POOLED &&
+      (!a_argmax || a_group < 32 || a_group > 256 || a_group % 32 != 0 || rows % a_group != 0 || m % 128 != 0))
+    return CODA_EINVAL;     // a 32-row slab must lie in one group; the group rows are staged 128 columns at a time
   if (b_mode == CODA_A32_AFFINE_RELU && (!b_scale || !b_shift)) return CODA_EINVAL;
   TN32Maps maps;
   int st = make_tmap_f32_box(&maps.a, a, m, rows, lda, 32, BKR);

@@ -131,16 +131,30 @@ bn_stats_partial_kernel(long long rows, int c, const float *__restrict__ y, floa
     p[cq + c4] = acc[1];
   }
 }
-__global__ void bn_stats_finalize_kernel(int nblocks, long long rows, int c, const float *__restrict__ partial,
-                                         float eps, float momentum, float *running_mean, float *running_var,
-                                         float *__restrict__ mean, float *__restrict__ invstd) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
+// one WARP per channel: lanes stride over the block partials (fp64), then a shuffle tree
+__device__ __forceinline__ void warp_partials_sum(int nblocks, int c, int ch, const float *__restrict__ partial,
+                                                  double &s, double &q) {
+  const int lane = threadIdx.x & 31;
+  s = 0.0; q = 0.0;
+  for (int b = lane; b < nblocks; b += 32) {
     s += (double)partial[(size_t)b * 2 * c + ch];
     q += (double)partial[(size_t)b * 2 * c + c + ch];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+}
+__global__ void __launch_bounds__(256)
+bn_stats_finalize_kernel(int nblocks, long long rows, int c, const float *__restrict__ partial,
+                         float eps, float momentum, float *running_mean, float *running_var,
+                         float *__restrict__ mean, float *__restrict__ invstd) {
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (ch >= c) return;
+  double s, q;
+  warp_partials_sum(nblocks, c, ch, partial, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   const double n = (double)rows, m = s / n;
   double var = q / n - m * m;
   if (var < 0.0) var = 0.0;
@@ -153,23 +167,22 @@ __global__ void bn_stats_finalize_kernel(int nblocks, long long rows, int c, con
 // finalisation of per-CTA partials written by a GEMM epilogue (coda_gemm_a32 col_stats): statistics + running
 // buffers as above, plus the folded per-channel affine map of BatchNorm: scale = gamma * invstd,
 // shift = beta - mean * scale (what the next GEMM's prologue applies), zero-padded up to cpad
-__global__ void bn_stats_finalize_affine_kernel(int nblocks, long long rows, int c, int cpad,
+__global__ void __launch_bounds__(256)
+bn_stats_finalize_affine_kernel(int nblocks, long long rows, int c, int cpad,
                                                 const float *__restrict__ partial, float eps, float momentum,
                                                 float *running_mean, float *running_var, const float *__restrict__ gamma,
                                                 const float *__restrict__ beta, float *__restrict__ mean,
                                                 float *__restrict__ invstd, float *__restrict__ scale,
                                                 float *__restrict__ shift) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (ch >= cpad) return;
   if (ch >= c) {
-    if (scale) { scale[ch] = 0.f; shift[ch] = 0.f; }
+    if (scale && (threadIdx.x & 31) == 0) { scale[ch] = 0.f; shift[ch] = 0.f; }
     return;
   }
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += (double)partial[(size_t)b * 2 * c + ch];
-    q += (double)partial[(size_t)b * 2 * c + c + ch];
-  }
+  double s, q;
+  warp_partials_sum(nblocks, c, ch, partial, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   const double n = (double)rows, m = s / n;
   double var = q / n - m * m;
   if (var < 0.0) var = 0.0;
@@ -337,17 +350,17 @@ bn_relu_bwd_reduce_pooled_kernel(long long groups, int group, int c, const float
     p[cq + c4] = acc[1];
   }
 }
-__global__ void sums_finalize_kernel(int nblocks, int c, const float *__restrict__ partial, float *__restrict__ s1,
-                                     float *__restrict__ s2) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+sums_finalize_kernel(int nblocks, int c, const float *__restrict__ partial, float *__restrict__ s1,
+                     float *__restrict__ s2) {
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (ch >= c) return;
-  double a = 0.0, b = 0.0;
-  for (int k = 0; k < nblocks; ++k) {
-    a += (double)partial[(size_t)k * 2 * c + ch];
-    b += (double)partial[(size_t)k * 2 * c + c + ch];
+  double a, b;
+  warp_partials_sum(nblocks, c, ch, partial, a, b);
+  if ((threadIdx.x & 31) == 0) {
+    s1[ch] = (float)a;
+    s2[ch] = (float)b;
   }
-  s1[ch] = (float)a;
-  s2[ch] = (float)b;
 }
 
 // ------------------------------------------------------------------ backward, second half
@@ -471,7 +484,7 @@ int coda_bn_rows_stats(long long rows, int c, const float *y, float eps, float m
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = grid_for(rows, c);
   bn_stats_partial_kernel<<<grid, THREADS, 0, s>>>(rows, c, y, scratch);
-  bn_stats_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>((int)grid, rows, c, scratch, eps, momentum, running_mean,
+  bn_stats_finalize_kernel<<<(c + 7) / 8, 256, 0, s>>>((int)grid, rows, c, scratch, eps, momentum, running_mean,
                                                            running_var, mean, invstd);
   return coda::launch_status();
 }
@@ -485,7 +498,7 @@ int coda_bn_rows_stats_affine(long long rows, int c, const float *y, float eps, 
   const unsigned grid = grid_for(rows, c);
   bn_stats_partial_kernel<<<grid, THREADS, 0, s>>>(rows, c, y, scratch);
   const int cpad = (c + 63) / 64 * 64;
-  bn_stats_finalize_affine_kernel<<<(cpad + 127) / 128, 128, 0, s>>>((int)grid, rows, c, cpad, scratch, eps, momentum,
+  bn_stats_finalize_affine_kernel<<<(cpad + 7) / 8, 256, 0, s>>>((int)grid, rows, c, cpad, scratch, eps, momentum,
                                                                     running_mean, running_var, gamma, beta, mean,
                                                                     invstd, scale, shift);
   return coda::launch_status();
@@ -497,7 +510,7 @@ int coda_bn_stats_finalize(int nblocks, long long rows, int c, const float *part
   if (nblocks <= 0 || rows <= 0 || c <= 0 || !partial || !mean || !invstd) return CODA_EINVAL;
   if ((scale != nullptr) != (shift != nullptr) || (scale && (!gamma || !beta))) return CODA_EINVAL;
   const int cpad = (c + 63) / 64 * 64;
-  bn_stats_finalize_affine_kernel<<<(cpad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  bn_stats_finalize_affine_kernel<<<(cpad + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
       nblocks, rows, c, cpad, partial, eps, momentum, running_mean, running_var, gamma, beta, mean, invstd, scale, shift);
   return coda::launch_status();
 }
@@ -557,7 +570,7 @@ int coda_bn_relu_bwd_reduce(long long rows, int c, const float *y, const float *
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = grid_for(rows, c);
   bn_relu_bwd_reduce_kernel<<<grid, THREADS, 0, s>>>(rows, c, y, dz, mean, invstd, gamma, beta, scratch);
-  sums_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>((int)grid, c, scratch, s1, s2);
+  sums_finalize_kernel<<<(c + 7) / 8, 256, 0, s>>>((int)grid, c, scratch, s1, s2);
   return coda::launch_status();
 }
 
@@ -572,7 +585,7 @@ int coda_bn_relu_bwd_reduce_pooled(long long groups, int group, int c, const flo
   const unsigned grid = grid_for(groups, c);
   bn_relu_bwd_reduce_pooled_kernel<<<grid, THREADS, 0, s>>>(groups, group, c, y, dpooled, argmax, mean, invstd, gamma,
                                                            beta, scratch);
-  sums_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>((int)grid, c, scratch, s1, s2);
+  sums_finalize_kernel<<<(c + 7) / 8, 256, 0, s>>>((int)grid, c, scratch, s1, s2);
   return coda::launch_status();
 }
 

@@ -154,17 +154,26 @@ bn_act_bwd_reduce_kernel(long long rows, int c, const float *__restrict__ y, con
     }
   }
 }
-__global__ void sums_finalize_kernel(int nblocks, int c, const float *__restrict__ partial, float *__restrict__ s1,
-                                     float *__restrict__ s2) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel: lanes stride over the block partials (fp64), then a shuffle tree
+__global__ void __launch_bounds__(256)
+sums_finalize_kernel(int nblocks, int c, const float *__restrict__ partial, float *__restrict__ s1,
+                     float *__restrict__ s2) {
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (ch >= c) return;
   double a = 0.0, b = 0.0;
-  for (int k = 0; k < nblocks; ++k) {
+  for (int k = lane; k < nblocks; k += 32) {
     a += (double)partial[(size_t)k * 2 * c + ch];
     b += (double)partial[(size_t)k * 2 * c + c + ch];
   }
-  s1[ch] = (float)a;
-  s2[ch] = (float)b;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    s1[ch] = (float)a;
+    s2[ch] = (float)b;
+  }
 }
 
 __global__ void __launch_bounds__(THREADS)
@@ -318,7 +327,7 @@ int coda_bn_act_rows_bwd_reduce(long long rows, int c, const float *y, const flo
   const unsigned grid = grid_for(rows, c);
   bn_act_bwd_reduce_kernel<<<grid, THREADS, 0, s>>>(rows, c, y, dout, mean, invstd, gamma, beta, relu, p, salt, seed,
                                                     scratch);
-  sums_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>((int)grid, c, scratch, s1, s2);
+  sums_finalize_kernel<<<(c + 7) / 8, 256, 0, s>>>((int)grid, c, scratch, s1, s2);
   return coda::launch_status();
 }
 

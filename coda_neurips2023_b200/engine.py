@@ -119,10 +119,9 @@ class BucketedAllReduce:
         active = [True] * n if active is None else list(active)
         total = flat.flat_grad.numel()
         # bucket boundaries at parameter boundaries, ~equal element counts
-        bounds, target, acc = [0], total / max(nbuckets, 1), 0
-        for i, p in enumerate(flat.params):
-            acc += p.numel()
-            if acc >= target * len(bounds) and len(bounds) < nbuckets and i + 1 < n:
+        bounds, target = [0], total / max(nbuckets, 1)
+        for i in range(n - 1):
+            if flat.offsets[i + 1] >= target * len(bounds) and len(bounds) < nbuckets:
                 bounds.append(flat.offsets[i + 1])
         bounds.append(total)
         self.ranges = list(zip(bounds[:-1], bounds[1:]))

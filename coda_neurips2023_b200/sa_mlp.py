@@ -230,9 +230,16 @@ class _SharedMLPMax(torch.autograd.Function):
                 check(L.coda_bn_bwd_coefs(_i(cout), _ll(rows), ptr(mean), ptr(invstd), ptr(gamma), ptr(s1), ptr(s2),
                                           ptr(alpha), ptr(bcoef), stream_of(x)), "bn_bwd_coefs")
                 pro = dict(a_scale=scales[li], a_shift=shifts[li], a_alpha=alpha, a_beta=bcoef)
-                if pooled_form:
+                if pooled_form and group % 32 == 0 and (128 % group == 0 or group % 128 == 0) and cout % 128 == 0:
+                    # the arg-max rows / pooled gradient of a tile's groups travel with the raw tiles (TMA)
                     mode, a2 = ops.A32_BN_BWD_POOLED, dpooled
                     extra = dict(argmax=argmax, group=group)
+                elif pooled_form:
+                    # group sizes that do not tile the kernels' 32-row slabs: expand the pooled gradient once
+                    dz = torch.zeros((rows // group, group, cout), dtype=torch.float32, device=dev)
+                    dz.scatter_(1, argmax.long().unsqueeze(1), dpooled.unsqueeze(1))
+                    dz = dz.view(rows, cout)
+                    mode, a2, extra = ops.A32_BN_BWD, dz, {}
                 else:
                     mode, a2, extra = ops.A32_BN_BWD, dz, {}
                 # dW = dy^T a_{l-1}: both operands are read as fp32 rows; a_{l-1} = relu(bn(y_{l-1})) (or x)
