@@ -108,9 +108,11 @@ class FlatParameters:
 
 class BucketedAllReduce:
     """Mean of the flat gradient over ranks as `nbuckets` all-reduces over contiguous ranges, each started (async,
-    on the process group's stream) by the post-accumulate hook of the LAST parameter of its range to receive its
-    gradient; `finish()` starts whatever is left and joins.  With the flat buffer laid out in gradient-ready
-    order the ranges complete front to back."""
+    on the process group's stream) the moment its range has received all of its gradient writes -- counted as
+    EVENTS: a post-accumulate hook of a parameter that autograd accumulates, or a direct write of a backward kernel
+    into the flat buffer (ops.GradSink).  The number of events per range is either the number of active parameters
+    (default) or measured on a calibration pass (`calibrate`).  `finish()` starts whatever is left and joins.  With
+    the flat buffer laid out in gradient-ready order the ranges complete front to back."""
 
     def __init__(self, flat: FlatParameters, nbuckets: int = 4, active=None):
         self.flat, self.world = flat, get_world_size()
@@ -125,9 +127,8 @@ class BucketedAllReduce:
                 bounds.append(flat.offsets[i + 1])
         bounds.append(total)
         self.ranges = list(zip(bounds[:-1], bounds[1:]))
-        self.bucket_of = []
-        for i in range(n):
-            self.bucket_of.append(next(b for b, (lo, hi) in enumerate(self.ranges) if lo <= flat.offsets[i] < hi))
+        self._starts = [lo for lo, _ in self.ranges]
+        self.bucket_of = [self.bucket_at(flat.offsets[i]) for i in range(n)]
         self.expected = [0] * len(self.ranges)
         for i in range(n):
             if active[i]:
@@ -135,20 +136,45 @@ class BucketedAllReduce:
         self.count = [0] * len(self.ranges)
         self.launched = [False] * len(self.ranges)
         self.works = []
+        self.calibrating = False
         self._avg = dist.ReduceOp.AVG if (self.enabled and dist.get_backend() == "nccl") else None
         if self.enabled:
             for i, p in enumerate(flat.params):
                 p.register_post_accumulate_grad_hook(self._make_hook(self.bucket_of[i]))
 
+    def bucket_at(self, elem_offset: int) -> int:
+        import bisect
+
+        return bisect.bisect_right(self._starts, elem_offset) - 1
+
     def _make_hook(self, b):
         def hook(_param):
-            self.count[b] += 1
-            if self.count[b] == self.expected[b]:
-                self._launch(b)
+            self.event(b)
         return hook
 
+    def event(self, b: int):
+        self.count[b] += 1
+        if not self.calibrating and self.count[b] == self.expected[b]:
+            self._launch(b)
+
+    def event_at(self, elem_offset: int):
+        """a backward kernel wrote the gradient region that starts at `elem_offset` of the flat buffer"""
+        if self.enabled:
+            self.event(self.bucket_at(elem_offset))
+
+    def calibrate(self, run_backward):
+        """Counts the gradient events per range on one forward/backward (`run_backward()`)."""
+        self.start()
+        self.calibrating = True
+        try:
+            run_backward()
+        finally:
+            self.calibrating = False
+        self.expected = list(self.count)
+        self.start()
+
     def _launch(self, b):
-        if self.launched[b]:
+        if self.launched[b] or not self.enabled:
             return
         self.launched[b] = True
         lo, hi = self.ranges[b]
@@ -336,17 +362,23 @@ class TrainStep:
                 order.append(p)
 
         handles = [p.register_post_accumulate_grad_hook(hook) for _, p in named]
+        sink = ops.GradSink()            # count mode: which parameter regions does the backward write, how often
+        sink.watch([p for _, p in named])
+        ops.set_grad_sink(sink)
         snap = self._snapshot()
         for _, p in named:
             p.grad = None
-        self._draw_selection(example_batch["point_clouds"].shape[0])
-        outputs = self.model(example_batch, curr_epoch=0)
-        loss, _ = self.criterion(outputs, dict(example_batch))
-        loss.backward()
+
+        def dry_run():
+            self._draw_selection(example_batch["point_clouds"].shape[0])
+            outputs = self.model(example_batch, curr_epoch=0)
+            loss, _ = self.criterion(outputs, dict(example_batch))
+            loss.backward()
+
+        dry_run()
         for h in handles:
             h.remove()
         self._restore(snap)
-        del outputs, loss
         inactive = [p for _, p in named if id(p) not in fired]
         if is_distributed() and self.world > 1:
             # every rank must lay the buffers out identically: compare the ready order with rank 0's
@@ -368,7 +400,20 @@ class TrainStep:
         self.optimizer = FlatAdamW(self.flat, self.lr, wds, active, max_norm=float(a.clip_gradient))
         self.reducer = BucketedAllReduce(self.flat, self.nbuckets, active)
         self.inactive_names = [n for n, f in zip(self.flat.names, active) if not f]
+        # from now on the backward kernels write single-use parameter gradients straight into flat_grad
+        flat_off = {id(p): off for p, off in zip(self.flat.params, self.flat.offsets)}
+        sink.arm(self.flat.flat_param, self.flat.flat_grad, [flat_off[id(p)] * 4 for _, p in named])
+        sink.on_write = self.reducer.event_at
+        self.sink = sink
         ops.invalidate_weight_cache()
+        if self.reducer.enabled:
+            # gradient events per all-reduce range (hooks + direct writes), measured once
+            snap = self._snapshot()
+            self.flat.zero_grad()
+            self.reducer.calibrate(dry_run)
+            self._restore(snap)
+            self.flat.zero_grad()
+            ops.invalidate_weight_cache()
         return self
 
     def capture(self, example_batch: dict, warmup: int = 3, curr_epoch: float = 0.0):

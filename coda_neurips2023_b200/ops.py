@@ -27,6 +27,92 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+# --------------------------------------------------------------------------- gradient sink
+class GradSink:
+    """Lets the backward kernels write PARAMETER gradients straight into the flat gradient buffer of
+    engine.FlatParameters instead of returning them to autograd (which would run one `grad += new` kernel per
+    parameter and zero-filled scatter kernels for sliced weights).  A parameter tensor -- or a contiguous slice /
+    reshape of one, e.g. the q / k / v row blocks of a packed in-projection -- is recognised by its address inside
+    the flat parameter buffer; only regions that receive exactly ONE gradient contribution per step are eligible
+    (measured on the probe pass), the others keep going through autograd's accumulation.
+
+    mode "count": record which regions the backward touches (probe pass, nothing is redirected);
+    mode "write": `lookup` returns the gradient view to write into, `wrote` notifies the all-reduce bucketing."""
+
+    def __init__(self):
+        self.mode = "count"
+        self.uses: dict = {}            # (param index, byte offset inside the parameter, numel) -> contributions
+        self._by_storage: dict = {}     # untyped storage address -> (param index, param)
+        self.base = self.end = 0
+        self.flat_grad = None
+        self.allowed: set = set()       # (byte offset in the flat buffer, numel)
+        self.on_write = None
+
+    # -- probe pass (parameters still own their storages)
+    def watch(self, params):
+        self._by_storage = {p.untyped_storage().data_ptr(): (i, p) for i, p in enumerate(params)}
+
+    def _note(self, w):
+        hit = self._by_storage.get(w.untyped_storage().data_ptr())
+        if hit is not None and w.is_contiguous():
+            key = (hit[0], w.data_ptr() - hit[1].data_ptr(), w.numel())
+            self.uses[key] = self.uses.get(key, 0) + 1
+
+    # -- steady state
+    def arm(self, flat_param, flat_grad, param_byte_offsets):
+        """param_byte_offsets[i]: byte offset of probe-time parameter i inside the flat buffers"""
+        self.base, self.end = flat_param.data_ptr(), flat_param.data_ptr() + flat_param.numel() * 4
+        self.flat_param = flat_param      # kept alive: its address range must not be recycled while this sink is armed
+        self.flat_grad = flat_grad
+        per_param: dict = {}
+        for (i, rel, numel), n in self.uses.items():
+            per_param.setdefault(i, []).append((rel, numel, n))
+        self.allowed = set()
+        for i, regions in per_param.items():
+            # eligible: every region of the parameter written once, regions pairwise disjoint
+            regions.sort()
+            ok = all(n == 1 for _, _, n in regions) and all(
+                a[0] + a[1] * 4 <= b[0] for a, b in zip(regions, regions[1:]))
+            if ok:
+                for rel, numel, _ in regions:
+                    self.allowed.add((param_byte_offsets[i] + rel, numel))
+        self.mode = "write"
+
+    def lookup(self, w):
+        if self.mode == "count":
+            self._note(w)
+            return None
+        ptr_ = w.data_ptr()
+        if not (self.base <= ptr_ < self.end) or not w.is_contiguous():
+            return None
+        off = ptr_ - self.base
+        if (off, w.numel()) not in self.allowed:
+            return None
+        return self.flat_grad.as_strided(w.shape, w.stride(), off // 4)
+
+    def wrote(self, view):
+        if self.on_write is not None:
+            self.on_write((view.data_ptr() - self.flat_grad.data_ptr()) // 4)
+
+
+_SINK: GradSink | None = None
+
+
+def set_grad_sink(sink) -> None:
+    global _SINK
+    _SINK = sink
+
+
+def _sink(w):
+    """Gradient destination of parameter(-slice) `w` in the flat buffer, or None (-> return the gradient to autograd)."""
+    return None if (_SINK is None or w is None) else _SINK.lookup(w)
+
+
+def _sunk(view):
+    _SINK.wrote(view)
+    return None      # what the backward returns to autograd for this input
+
+
 # --------------------------------------------------------------------------- LayerNorm
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
@@ -42,24 +128,29 @@ class _LayerNorm(torch.autograd.Function):
             st = lib().coda_layer_norm_fwd(_ll(rows), _i(c), _f(eps), ptr(xc), ptr(weight), ptr(bias), ptr(y),
                                            ptr(mean), ptr(rstd), stream_of(x))
         check(st, "layer_norm_fwd")
-        ctx.save_for_backward(xc, weight, mean, rstd)
+        ctx.save_for_backward(xc, weight, bias, mean, rstd)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        xc, weight, mean, rstd = ctx.saved_tensors
+        xc, weight, bias, mean, rstd = ctx.saved_tensors
         dyc = _f32c(dy)
         c = xc.shape[-1]
         rows = xc.numel() // c
         dx = torch.empty_like(xc)
-        dgamma = torch.empty_like(weight)
-        dbeta = torch.empty_like(weight)
+        sg, sb = _sink(weight), _sink(bias)
+        if sg is None or sb is None:
+            sg = sb = None
+        dgamma = torch.empty_like(weight) if sg is None else sg
+        dbeta = torch.empty_like(weight) if sb is None else sb
         nscratch = lib().coda_layer_norm_bwd_scratch(_ll(rows), _i(c))
         partial = torch.empty(max(int(nscratch), 1), dtype=torch.float32, device=xc.device)
         with torch.cuda.device(xc.device):
             st = lib().coda_layer_norm_bwd(_ll(rows), _i(c), ptr(dyc), ptr(xc), ptr(weight), ptr(mean), ptr(rstd),
                                            ptr(dx), ptr(dgamma), ptr(dbeta), ptr(partial), stream_of(xc))
         check(st, "layer_norm_bwd")
+        if sg is not None:
+            return dx, _sunk(sg), _sunk(sb), None
         return dx, dgamma, dbeta, None
 
 
@@ -198,8 +289,11 @@ class _BNActRows(torch.autograd.Function):
         dc = _f32c(dout)
         rows, c = y.shape
         dev = y.device
-        s1 = torch.empty(c, dtype=torch.float32, device=dev)
-        s2 = torch.empty(c, dtype=torch.float32, device=dev)
+        sg, sb = _sink(gamma), _sink(beta)
+        if sg is None or sb is None:
+            sg = sb = None
+        s1 = torch.empty(c, dtype=torch.float32, device=dev) if sb is None else sb      # dbeta
+        s2 = torch.empty(c, dtype=torch.float32, device=dev) if sg is None else sg      # dgamma
         dy = torch.empty_like(y)
         L = lib()
         seed = ptr(_seed_dev(dev) if ctx.p > 0 else None)
@@ -209,6 +303,8 @@ class _BNActRows(torch.autograd.Function):
             check(L.coda_bn_act_rows_bwd_reduce(*args, ptr(s1), ptr(s2), ptr(_bn_scratch(c, dev)), stream_of(y)),
                   "bn_act_rows_bwd_reduce")
             check(L.coda_bn_act_rows_bwd(*args, ptr(s1), ptr(s2), ptr(dy), stream_of(y)), "bn_act_rows_bwd")
+        if sg is not None:
+            return dy, _sunk(sg), _sunk(sb), None, None, None, None
         return dy, s2, s1, None, None, None, None      # dgamma = sum dz * xhat, dbeta = sum dz
 
 
@@ -483,7 +579,7 @@ def tn32_ok(a: torch.Tensor) -> bool:
 
 def gemm_tn32(a: torch.Tensor, b: torch.Tensor, *, a_mode: int = A32_PLAIN, a_scale=None, a_shift=None, a_alpha=None,
               a_beta=None, a2=None, argmax=None, group: int = 0, b_mode: int = A32_PLAIN, b_scale=None,
-              b_shift=None) -> torch.Tensor:
+              b_shift=None, out: torch.Tensor | None = None) -> torch.Tensor:
     """C (m, n) = sum_r TA(a)[r, :]^T TB(b)[r, :] from the fp32 activations a (R, m), b (R, n) read in place
     (csrc/gemm_tn32_sm100.cu): the weight-gradient GEMM with the BatchNorm-backward / BatchNorm-forward
     prologues applied inside the kernel.  Two bf16 planes per operand."""
@@ -491,7 +587,9 @@ def gemm_tn32(a: torch.Tensor, b: torch.Tensor, *, a_mode: int = A32_PLAIN, a_sc
     rows, m = a.shape
     n = b.shape[1]
     assert tn32_ok(a) and tn32_ok(b) and b.shape[0] == rows
-    out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    assert out.shape == (m, n) and out.stride(1) == 1 and out.stride(0) % 4 == 0 and out.data_ptr() % 16 == 0
     lda2 = 0
     if a_mode == A32_BN_BWD:
         assert a32_ok(a2) and a2.shape == a.shape
@@ -501,8 +599,8 @@ def gemm_tn32(a: torch.Tensor, b: torch.Tensor, *, a_mode: int = A32_PLAIN, a_sc
     with torch.cuda.device(a.device):
         st = lib().coda_gemm_tn32(_ll(rows), _i(m), _i(n), ptr(a), _ll(a.stride(0)), _i(a_mode), ptr(a_scale),
                                   ptr(a_shift), ptr(a_alpha), ptr(a_beta), ptr(a2), _ll(lda2), ptr(argmax), _i(group),
-                                  ptr(b), _ll(b.stride(0)), _i(b_mode), ptr(b_scale), ptr(b_shift), ptr(out), _ll(n),
-                                  stream_of(a))
+                                  ptr(b), _ll(b.stride(0)), _i(b_mode), ptr(b_scale), ptr(b_shift), ptr(out),
+                                  _ll(out.stride(0)), stream_of(a))
     check(st, "gemm_tn32")
     return out
 
@@ -574,14 +672,17 @@ def _packed_weight(w: torch.Tensor, transposed: bool, nsplit: int) -> torch.Tens
     return hit[0]
 
 
-def colsum(x: torch.Tensor) -> torch.Tensor:
-    """sum over the rows of a contiguous (rows, c) fp32 matrix (bias gradients); falls back to torch for channel
-    counts the row kernels do not cover."""
+def colsum(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """sum over the rows of a contiguous (rows, c) fp32 matrix (bias gradients).  Channel counts the row kernel does
+    not cover (the 2- / 3- / 12-wide prediction heads) take the plain tensor reduction."""
     rows, c = x.shape
     if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and rows > 0
             and 4 <= c <= 1024 and c % 4 == 0 and 256 % (c // 4) == 0):
-        return x.sum(dim=0)
-    out = torch.empty(c, dtype=torch.float32, device=x.device)
+        if out is None:
+            return x.sum(dim=0)
+        return torch.sum(x, dim=0, out=out)
+    if out is None:
+        out = torch.empty(c, dtype=torch.float32, device=x.device)
     scratch = torch.empty(148 * 4 * 2 * c, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         st = lib().coda_rows_colsum(_ll(rows), _i(c), ptr(x), ptr(out), ptr(scratch), stream_of(x))
@@ -605,13 +706,13 @@ class _Linear(torch.autograd.Function):
             y = gemm_a32(x, wp, n, bias=bias, relu=relu)
         else:          # rows TMA cannot address in place (k or n not a multiple of 4: the 2-/3-wide heads): packed operands
             y = gemm_nt(_packed_rows(x, nsplit), wp, m, n, bias=bias, relu=relu)[0]
-        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.save_for_backward(x, weight, y if relu else None, bias)
         ctx.has_bias, ctx.relu, ctx.nsplit = bias is not None, relu, nsplit
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, y = ctx.saved_tensors
+        x, weight, y, bias = ctx.saved_tensors
         # gradients are held to a looser bar than the forward (5e-3 vs 1e-4): two planes suffice
         nsplit = min(ctx.nsplit, BACKWARD_NSPLIT)
         dy = dy.contiguous()
@@ -629,13 +730,19 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             # dW (n, k) = sum_m dY[m, n] X[m, k]: contraction over the ROWS of both operands
             if tn32_ok(dy) and tn32_ok(x) and nsplit == 2:
-                dw = gemm_tn32(dy, x)            # fp32 rows in place, split inside the kernel
+                sw = _sink(weight) if k % 4 == 0 else None
+                dw = gemm_tn32(dy, x, out=sw)    # fp32 rows in place, split inside the kernel
+                if sw is not None:
+                    dw = _sunk(sw)
             else:
                 dya = pack_split(dy, m, n, n, 1, nsplit)
                 xa = _packed_rows(x, nsplit)     # shared by every layer that consumed the same x (the six heads)
                 dw = gemm_tn(dya, xa, n, k)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dy)
+            sb = _sink(bias)
+            db = colsum(dy, out=sb)
+            if sb is not None:
+                db = _sunk(sb)
         return dx, dw, db, None, None
 
 

@@ -195,8 +195,11 @@ class _SharedMLPMax(torch.autograd.Function):
                 w, gamma, beta = params[3 * li: 3 * li + 3]
                 cout, cin = w.shape
                 y, mean, invstd = ys[li], means[li], invstds[li]
-                s1 = torch.empty(cout, dtype=torch.float32, device=dev)
-                s2 = torch.empty(cout, dtype=torch.float32, device=dev)
+                sg, sb = ops._sink(gamma), ops._sink(beta)       # dgamma / dbeta straight into the flat gradient buffer
+                if sg is None or sb is None:
+                    sg = sb = None
+                s1 = torch.empty(cout, dtype=torch.float32, device=dev) if sb is None else sb
+                s2 = torch.empty(cout, dtype=torch.float32, device=dev) if sg is None else sg
                 scratch = _scratch(cout, dev)
                 pooled_form = li == nl - 1
                 if pooled_form:
@@ -208,7 +211,11 @@ class _SharedMLPMax(torch.autograd.Function):
                     check(L.coda_bn_relu_bwd_reduce(_ll(rows), _i(cout), ptr(y), ptr(dz), ptr(mean), ptr(invstd),
                                                     ptr(gamma), ptr(beta), ptr(s1), ptr(s2), ptr(scratch), stream_of(x)),
                           "bn_relu_bwd_reduce")
-                grads[3 * li + 1], grads[3 * li + 2] = s2, s1            # dgamma, dbeta
+                if sg is None:
+                    grads[3 * li + 1], grads[3 * li + 2] = s2, s1        # dgamma, dbeta
+                else:
+                    ops._sunk(sg), ops._sunk(sb)
+                sw = ops._sink(w)
                 if li == 0 and ctx.small_k:
                     if nl == 1:   # single block: expand the pooled gradient (not a CoDA configuration)
                         dz = torch.zeros((rows // group, group, cout), dtype=torch.float32, device=dev)
@@ -217,12 +224,14 @@ class _SharedMLPMax(torch.autograd.Function):
                     L.coda_bn_rows_small_k_scratch_floats.restype = ctypes.c_longlong
                     sc = torch.empty(int(L.coda_bn_rows_small_k_scratch_floats(_i(cin), _i(cout))), dtype=torch.float32,
                                      device=dev)
-                    dw = torch.empty((cout, cin), dtype=torch.float32, device=dev)
+                    dw = torch.empty((cout, cin), dtype=torch.float32, device=dev) if sw is None else sw
                     check(L.coda_bn_relu_bwd_small_k(_ll(rows), _i(cin), _i(cout), ptr(y), ptr(dz), ptr(mean), ptr(invstd),
                                                      ptr(gamma), ptr(beta), ptr(s1), ptr(s2), ptr(x), ptr(dw), ptr(sc),
                                                      stream_of(x)), "bn_relu_bwd_small_k")
-                    grads[0] = dw
+                    grads[0] = dw if sw is None else ops._sunk(sw)
                     break
+                if sw is not None and cin % 4 != 0:
+                    sw = None
                 # BatchNorm(+ReLU) backward as a GEMM prologue: dy = [z > 0] * scale * d + alpha * y + beta
                 cpad = ops._pad64(cout)
                 alpha = torch.empty(cpad, dtype=torch.float32, device=dev)
@@ -245,9 +254,11 @@ class _SharedMLPMax(torch.autograd.Function):
                 # dW = dy^T a_{l-1}: both operands are read as fp32 rows; a_{l-1} = relu(bn(y_{l-1})) (or x)
                 if li > 0:
                     grads[3 * li] = ops.gemm_tn32(y, ys[li - 1], a_mode=mode, a2=a2, b_mode=ops.A32_AFFINE_RELU,
-                                                  b_scale=scales[li - 1], b_shift=shifts[li - 1], **pro, **extra)
+                                                  b_scale=scales[li - 1], b_shift=shifts[li - 1], out=sw, **pro, **extra)
                 else:
-                    grads[3 * li] = ops.gemm_tn32(y, x, a_mode=mode, a2=a2, **pro, **extra)
+                    grads[3 * li] = ops.gemm_tn32(y, x, a_mode=mode, a2=a2, out=sw, **pro, **extra)
+                if sw is not None:
+                    grads[3 * li] = ops._sunk(sw)
                 if li > 0 or ctx.needs_input_grad[0]:
                     # dz_{l-1} = dy W_l: the forward weight planes as an MN-major operand
                     dz_new = ops.gemm_a32(y, ops._packed_weight(w, False, ctx.nsplit), cin, mode=mode, scale=scales[li],
