@@ -75,6 +75,7 @@ struct A32Params {
   const float *bias;
   int act;
   float *stats;            // [gridDim.x][2][n] or null
+  int b_resident;          // the whole B operand of this CTA's n-tile stays in shared memory (short contractions)
 };
 
 // 32 values per lane (one row each) -> lane j ends with the sum over the warp's 32 rows of value j
@@ -129,9 +130,22 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
   const long long nwork = (long long)tiles_m * tiles_n;
   const int nkb = (P.k + BK - 1) / BK;
   // n runs fastest: the n-tiles of one m-tile are in flight together on neighbouring CTAs, A comes from HBM once
-  auto decode = [&](long long w, int &m0, int &n0) {
+  // B-resident mode: a CTA keeps ONE n-tile for its whole life (its B planes are loaded once and never leave
+  // shared memory) and walks the m-tiles with stride gridDim / tiles_n.
+  auto tile_at = [&](long long t, int &m0, int &n0) -> bool {
+    if (P.b_resident) {
+      const int per = (int)gridDim.x / tiles_n;
+      const long long tm = (long long)(blockIdx.x / tiles_n) + t * per;
+      if ((int)blockIdx.x >= per * tiles_n || tm >= tiles_m) return false;
+      m0 = (int)tm * BM;
+      n0 = (int)(blockIdx.x % tiles_n) * BN;
+      return true;
+    }
+    const long long w = blockIdx.x + t * gridDim.x;
+    if (w >= nwork) return false;
     n0 = (int)(w % tiles_n) * BN;
     m0 = (int)(w / tiles_n) * BM;
+    return true;
   };
 
   if (warp == 0 && lane == 0) {
@@ -162,13 +176,31 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
   if (warp == 0) {
     // ===== TMA producer =====
     uint32_t it = 0;
-    for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
-      int m0, n0;
-      decode(w, m0, n0);
+    int m0, n0;
+    auto load_b = [&](int kb, int bs) {
+      unsigned char *bt = b_ring + (size_t)bs * B_STAGE;
+      mbar_arrive_expect_tx(&b_full[bs], (uint32_t)B_STAGE);
+#pragma unroll
+      for (int p = 0; p < NSPLIT; ++p) {
+        if (!B_MN) {
+          tma_load_3d(bt + p * B_TILE, &maps.b[p], &b_full[bs], kb * BK, n0, 0);
+        } else {
+#pragma unroll
+          for (int g = 0; g < BN / 64; ++g)
+            tma_load_3d(bt + p * B_TILE + g * 8192, &maps.b[p], &b_full[bs], n0 + g * 64, kb * BK, 0);
+        }
+      }
+    };
+    if (P.b_resident && tile_at(0, m0, n0)) {
+      if (elect_one_sync())
+        for (int kb = 0; kb < nkb; ++kb) load_b(kb, kb);
+      __syncwarp();
+    }
+    for (long long t = 0; tile_at(t, m0, n0); ++t) {
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int rs = it % nraw, bs = it % B_STAGES;
         mbar_wait(&raw_empty[rs], ((it / nraw) & 1u) ^ 1u);
-        mbar_wait(&b_empty[bs], ((it / B_STAGES) & 1u) ^ 1u);
+        if (!P.b_resident) mbar_wait(&b_empty[bs], ((it / B_STAGES) & 1u) ^ 1u);
         if (elect_one_sync()) {
           unsigned char *rt = raw_ring + (size_t)rs * raw_stage_bytes;
           mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)(RAW_TILE * (two_in ? 2 : 1) + tile_groups * 320));
@@ -187,18 +219,7 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
             tma_load_3d(rt + RAW_TILE, &maps.a2, &raw_full[rs], kb * BK, m0, 0);
             tma_load_3d(rt + RAW_TILE + RAW_TILE / 2, &maps.a2, &raw_full[rs], kb * BK + 32, m0, 0);
           }
-          unsigned char *bt = b_ring + (size_t)bs * B_STAGE;
-          mbar_arrive_expect_tx(&b_full[bs], (uint32_t)B_STAGE);
-#pragma unroll
-          for (int p = 0; p < NSPLIT; ++p) {
-            if (!B_MN) {
-              tma_load_3d(bt + p * B_TILE, &maps.b[p], &b_full[bs], kb * BK, n0, 0);
-            } else {
-#pragma unroll
-              for (int g = 0; g < BN / 64; ++g)
-                tma_load_3d(bt + p * B_TILE + g * 8192, &maps.b[p], &b_full[bs], n0 + g * 64, kb * BK, 0);
-            }
-          }
+          if (!P.b_resident) load_b(kb, bs);
         }
         __syncwarp();
       }
@@ -207,15 +228,16 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = umma_idesc_f16(0, BM, BN, 0, B_MN ? 1 : 0);
     uint32_t it = 0, tile_i = 0;
-    for (long long w = blockIdx.x; w < nwork; w += gridDim.x, ++tile_i) {
+    int m0, n0;
+    for (long long t = 0; tile_at(t, m0, n0); ++t, ++tile_i) {
       const uint32_t buf = tile_i & 1u, use = tile_i >> 1;
       mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + buf * ACC_COLS;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int as = it % A_STAGES, bs = it % B_STAGES;
+        const int as = it % A_STAGES, bs = P.b_resident ? kb : (int)(it % B_STAGES);
         mbar_wait(&a_full[as], (it / A_STAGES) & 1u);
-        mbar_wait(&b_full[bs], (it / B_STAGES) & 1u);
+        mbar_wait(&b_full[bs], P.b_resident ? 0u : ((it / B_STAGES) & 1u));
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t a_t = tmem_a0 + (uint32_t)as * A_COLS;
@@ -231,7 +253,7 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
               umma_f16_ts(tmem_acc, at + kk * 8, umma_desc_advance(bd, kk * KSTEP), idesc, (uint32_t)((kb | p | kk) != 0));
           }
           umma_commit(&a_empty[as]);
-          umma_commit(&b_empty[bs]);
+          if (!P.b_resident) umma_commit(&b_empty[bs]);
           if (kb == nkb - 1) umma_commit(&acc_full[buf]);
         }
         __syncwarp();
@@ -244,9 +266,8 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int sw = row & 7;
     uint32_t it = 0;
-    for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
-      int m0, n0;
-      decode(w, m0, n0);
+    int m0, n0;
+    for (long long t = 0; tile_at(t, m0, n0); ++t) {
       const long long grow = (long long)m0 + row;     // global row (mode 3: its group / index within the group)
       int pgt = 0, pgi = 0;       // pooled mode: this row's group within the tile, its index within the group
       if (pooled) {
@@ -354,9 +375,8 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
     unsigned char *srow = stage + lane * 128;
     const int sw = lane & 7;
     float *my_stats = P.stats ? s_stats + (size_t)q * 2 * n : nullptr;
-    for (long long w = blockIdx.x; w < nwork; w += gridDim.x, ++tile_i) {
-      int m0, n0;
-      decode(w, m0, n0);
+    int m0, n0;
+    for (long long t = 0; tile_at(t, m0, n0); ++t, ++tile_i) {
       const uint32_t buf = tile_i & 1u, use = tile_i >> 1;
       const int row = m0 + q * 32 + lane;
       mbar_wait(&acc_full[buf], use & 1u);
@@ -464,9 +484,15 @@ int launch_a32(const A32Maps &maps, const A32Params &P, cudaStream_t s) {
     if (e != cudaSuccess) return (int)e;
     configured = SMEM_MAX;
   }
-  const long long nwork = (long long)((P.m + BM - 1) / BM) * ((P.n + BN - 1) / BN);
-  const unsigned grid = (unsigned)(nwork < num_sms() ? nwork : num_sms());
-  kern<<<grid, 384, total, s>>>(maps, P);
+  const int tiles_m = (P.m + BM - 1) / BM, tiles_n = (P.n + BN - 1) / BN;
+  const long long nwork = (long long)tiles_m * tiles_n;
+  unsigned grid = (unsigned)(nwork < num_sms() ? nwork : num_sms());
+  A32Params Q = P;
+  const int nkb = (P.k + BK - 1) / BK;
+  // short contraction, many m-tiles: keep the weights of one n-tile resident per CTA
+  Q.b_resident = (nkb <= B_STAGES && tiles_n <= num_sms() && tiles_m >= 4 * (num_sms() / tiles_n)) ? 1 : 0;
+  if (Q.b_resident) grid = (unsigned)((num_sms() / tiles_n) * tiles_n);
+  kern<<<grid, 384, total, s>>>(maps, Q);
   return launch_status();
 }
 
@@ -475,10 +501,9 @@ int launch_a32(const A32Maps &maps, const A32Params &P, cudaStream_t s) {
 extern "C" {
 
 int coda_gemm_a32_grid(int m, int n) {
+  // upper bound of the launch grid = rows of the (zero-initialised) col_stats buffer the caller provides
   if (m <= 0 || n <= 0) return 0;
-  const int bn = n <= 64 ? 64 : 128;
-  const long long nwork = (long long)((m + BM - 1) / BM) * ((n + bn - 1) / bn);
-  return (int)(nwork < num_sms() ? nwork : num_sms());
+  return num_sms();
 }
 
 int coda_gemm_a32(int nsplit, int m, int n, int k, const float *a, long long lda, int a_mode, const float *a_scale,
@@ -527,6 +552,7 @@ int coda_gemm_a32(int nsplit, int m, int n, int k, const float *a, long long lda
   A32Params P;
   P.m = m; P.n = n; P.k = k; P.mode = a_mode; P.scale = a_scale; P.shift = a_shift; P.alpha = a_alpha; P.beta = a_beta;
   P.dpooled = a2; P.argmax = a_argmax; P.group = a_group; P.bias = bias; P.act = act; P.stats = col_stats;
+  P.b_resident = 0;
   cudaStream_t s = (cudaStream_t)stream;
 #define CODA_A32(NS, BN_, RS, BS)                                                   \
   return b_mn ? launch_a32<NS, BN_, RS, BS, true>(maps, P, s) : launch_a32<NS, BN_, RS, BS, false>(maps, P, s)

@@ -23,7 +23,7 @@ namespace {
 constexpr int BM = 128;      // output rows per tile  (columns of A)
 constexpr int BKR = 32;      // contraction rows per pipeline stage
 constexpr int NS = 2;        // bf16 planes per operand (gradient precision, as the packed TN path)
-constexpr int RAW_STAGES = 2, PL_STAGES = 2;
+constexpr int RAW_STAGES = 3, PL_STAGES = 2;   // fp32 slabs in flight (HBM latency) / converted operand slabs
 
 struct TN32Maps {
   CUtensorMap a, a2, b, c;
@@ -83,7 +83,7 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char *raw_ring = smem;
   unsigned char *pl_ring = smem + (size_t)RAW_STAGES * RAW_STAGE;
-  unsigned char *epi = pl_ring + (size_t)PL_STAGES * PL_STAGE;      // 4 x [32 x 128 B]
+  unsigned char *epi = raw_ring;      // 4 x [32 x 128 B] staging tiles: the raw ring is idle once the last MMA is done
   __shared__ __align__(8) uint64_t raw_full[RAW_STAGES], raw_empty[RAW_STAGES];
   __shared__ __align__(8) uint64_t pl_full[PL_STAGES], pl_empty[PL_STAGES];
   __shared__ __align__(8) uint64_t acc_full;
@@ -314,7 +314,7 @@ inline int make_tmap_f32_box(CUtensorMap *map, const void *base, long long cols,
 template <int BN>
 int launch_tn32(const TN32Maps &maps, TN32Params P, float *c, long long ldc, cudaStream_t s) {
   constexpr size_t smem = (size_t)RAW_STAGES * (2 * BKR * BM * 4 + BKR * BN * 4 + 1024) +
-                          (size_t)PL_STAGES * NS * (BKR * BM * 2 + BKR * BN * 2) + 4 * 32 * 128 + 1024;
+                          (size_t)PL_STAGES * NS * (BKR * BM * 2 + BKR * BN * 2) + 1024;
   static_assert(smem <= 227 * 1024, "smem budget");
   auto kern = gemm_tn32_kernel<BN>;
   static bool configured = false;

@@ -557,7 +557,8 @@ def gemm_a32(a: torch.Tensor, b_planes: torch.Tensor, n: int, *, mode: int = A32
     L = lib()
     stats = None
     if want_stats:
-        stats = torch.empty((int(L.coda_gemm_a32_grid(_i(m), _i(n))), 2, n), dtype=torch.float32, device=a.device)
+        # rows = upper bound of the grid; CTAs that do not exist / columns a CTA never owns stay zero
+        stats = torch.zeros((int(L.coda_gemm_a32_grid(_i(m), _i(n))), 2, n), dtype=torch.float32, device=a.device)
     lda2 = 0
     if mode == A32_BN_BWD:
         assert a32_ok(a2) and a2.shape == a.shape

@@ -91,8 +91,8 @@ int coda_gemm_tn(int nsplit, int mc, int m, int n, const void *a, long long a_pl
  *                               argmax (m / group, k) uint8 = row within the group that produced the maximum
  * B: bf16 planes as produced by coda_pack_split_bf16, either K-major [n][b_ld] (b_mn = 0, b_ld >= pad64(k)) or
  * "MN-major" [k][b_ld] (b_mn = 1, b_ld >= n: the forward weight planes reused for the input gradient).
- * col_stats: NULL, or [coda_gemm_a32_grid(m, n)][2][n] floats that receive per-CTA partial column sums and sums of
- * squares of C (BatchNorm statistics of the layer just computed; n <= 512), to be finalised by
+ * col_stats: NULL, or a ZERO-INITIALISED [coda_gemm_a32_grid(m, n)][2][n] float buffer that receives per-CTA partial
+ * column sums and sums of squares of C (BatchNorm statistics of the layer just computed; n <= 512), to be finalised by
  * coda_bn_stats_finalize (coda_sa_mlp.h).
  */
 #define CODA_A32_PLAIN 0
