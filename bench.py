@@ -244,38 +244,72 @@ def _time_launch(fn, reps=20, warm=3):
     return e0.elapsed_time(e1) / reps
 
 
-def gemm_roofline(a, device):
-    """The dominant kernel by share of the step (profiles/r01_step_kernels_*.txt): the split-bf16 tcgen05 GEMM
-    instance gemm_nt_kernel<3,128,2> (every fp32 Linear / 1x1 conv forward), timed on its longest launch of the
-    step: the third set-abstraction layer, (B * 2048 seeds * 64 neighbours) rows x 128 -> 256 channels.  At this
-    shape the kernel streams: algorithmic bytes = the three bf16 planes of A read once + the fp32 output written
-    once (+ the 0.2 MB weight planes); peak = MEASURED_PEAKS.json hbm_gbs."""
+def _peaks():
+    try:
+        return json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except OSError:
+        return {}
+
+
+def sa_wgrad_roofline(a, device):
+    """The dominant kernel by share of the step (profiles/r02_step_kernels.txt: gemm_tn32_kernel<128>, every weight
+    gradient of the step, 11 %), timed alone on its longest launch: the weight gradient of the third set-abstraction
+    layer, dW2 (256 x 128) = dY2^T A2 over R = B * 2048 * 64 rows, with the step's prologues (dY2 from the pre-BN
+    activation y2 + the max-pooled gradient; A2 = relu(bn(y1))).  The kernel streams both fp32 activations once:
+    algorithmic bytes = 4 R (256 + 128) (+ 21 MB pooled gradient / arg-max); peak = MEASURED_PEAKS.json hbm_gbs."""
     from coda_neurips2023_b200 import ops
 
-    peaks = {}
-    try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except OSError:
-        pass
+    peaks = _peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    rows, k, n, ns = a.batch_per_gpu * 2048 * 64, 128, 256, a.nsplit
-    ap = torch.randn(ns, 1, rows, k, device=device).bfloat16()           # operand planes, as bn_relu_pack writes them
-    wp = ops.pack_split(torch.randn(n, k, device=device), n, k, k, 1, ns)
-    y = torch.empty(1, rows, n, device=device)
-    ms = _time_launch(lambda: ops.gemm_nt(ap, wp, rows, n, out=y))
-    nbytes = 2.0 * ns * rows * k + 4.0 * rows * n + 2.0 * ns * n * k
+    rows, m, n, group = a.batch_per_gpu * 2048 * 64, 256, 128, 64
+    y2 = torch.randn(rows, m, device=device)
+    y1 = torch.randn(rows, n, device=device)
+    dp = torch.randn(rows // group, m, device=device)
+    arg = torch.randint(0, group, (rows // group, m), device=device, dtype=torch.uint8)
+    v = lambda c: (torch.rand(c, device=device) + 0.5, torch.randn(c, device=device) * 0.1)  # noqa: E731
+    (sa, ta), (al, be), (sb, tb) = v(m), v(m), v(n)
+    out = torch.empty(m, n, device=device)
+    ms = _time_launch(lambda: ops.gemm_tn32(y2, y1, a_mode=ops.A32_BN_BWD_POOLED, a_scale=sa, a_shift=ta, a_alpha=al,
+                                            a_beta=be, a2=dp, argmax=arg, group=group, b_mode=ops.A32_AFFINE_RELU,
+                                            b_scale=sb, b_shift=tb, out=out))
+    nbytes = 4.0 * rows * (m + n) + 5.0 * (rows // group) * m + 4.0 * m * n
     achieved = nbytes / (ms * 1e-3) / 1e9
-    flops = 2.0 * rows * n * k
-    return {"bound": "hbm", "kernel": "gemm_nt_kernel<%d,128,2> (tcgen05 split-bf16 GEMM; SA layer 3: %d x %d x %d, "
-            "fp32-class result from %d bf16 planes)" % (ns, rows, n, k, ns),
+    return {"bound": "hbm", "kernel": "gemm_tn32_kernel<128> (tcgen05 weight-gradient GEMM on fp32 rows, BatchNorm-backward / "
+            "BatchNorm+ReLU prologues in-kernel; SA layer 3: dW (%d x %d) over %d rows)" % (m, n, rows),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
             "bytes_per_launch": nbytes, "ms_per_launch": ms,
-            "traffic": 1.89e9 if ns == 3 else None,
-            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this launch "
-                              "(profiles/r01_gemm_ncu.txt)" if ns == 3 else None,
-            "useful_tflops": flops / (ms * 1e-3) / 1e12,
-            "note": "working set (%.1f GB) >> 126 MB L2: every timed launch streams from HBM" % (nbytes / 1e9)}
+            "traffic": 1.632e9, "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this launch "
+                                                   "(profiles/r02_sa_mlp_traffic.txt)",
+            "useful_tflops": 2.0 * rows * m * n / (ms * 1e-3) / 1e12,
+            "note": "working set (1.6 GB) >> 126 MB L2: every timed launch streams from HBM"}
+
+
+def sa_forward_roofline(a, device):
+    """gemm_a32_kernel<3,128,...> on the forward of the same layer: y2 (R x 256) = relu(bn(y1)) W2^T, y1 read as fp32
+    with the BatchNorm+ReLU prologue, BatchNorm statistics of y2 produced by the epilogue.  Algorithmic bytes = y1 read
+    once + y2 written once."""
+    from coda_neurips2023_b200 import ops
+
+    peaks = _peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    rows, k, n, ns = a.batch_per_gpu * 2048 * 64, 128, 256, a.nsplit
+    y1 = torch.randn(rows, k, device=device)
+    wp = ops.pack_split(torch.randn(n, k, device=device) / k ** 0.5, n, k, k, 1, 3)
+    sc, sh = torch.rand(k, device=device) + 0.5, torch.randn(k, device=device) * 0.1
+    out = torch.empty(rows, n, device=device)
+    ms = _time_launch(lambda: ops.gemm_a32(y1, wp, n, mode=ops.A32_AFFINE_RELU, scale=sc, shift=sh, out=out,
+                                           want_stats=True, nsplit=ns))
+    nbytes = 4.0 * rows * (k + n) + 2.0 * ns * n * k
+    achieved = nbytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "gemm_a32_kernel<%d,128> (tcgen05 GEMM, fp32 A split in-kernel into TMEM, BN+ReLU "
+            "prologue, BN-statistics epilogue; SA layer 3 forward: %d x %d x %d)" % (ns, rows, n, k),
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+            "bytes_per_launch": nbytes, "ms_per_launch": ms, "traffic": 1.549e9,
+            "traffic_source": "ncu dram bytes of this launch (profiles/r02_sa_mlp_traffic.txt)",
+            "useful_tflops": 2.0 * rows * n * k / (ms * 1e-3) / 1e12,
+            "tensor_pipe_tflops": 2.0 * rows * n * k * {2: 3, 3: 6}[ns] / (ms * 1e-3) / 1e12}
 
 
 def run_ours(a):
@@ -397,9 +431,9 @@ def run_ours(a):
         "operand_split": a.nsplit, "param_spread_across_ranks": param_spread,
         "grad_allreduce_bytes": step.flat.nbytes(),
     }
-    line["roofline"] = gemm_roofline(a, device)
-    # the tensor-bound kernels next in line, same measurement method (kernel alone, CUDA events)
-    line["roofline_more"] = [attention_roofline(a, device)]
+    line["roofline"] = sa_wgrad_roofline(a, device)
+    # the kernels next in line, same measurement method (kernel alone, CUDA events)
+    line["roofline_more"] = [sa_forward_roofline(a, device), attention_roofline(a, device)]
     if world == 1 and not a.no_cpu_baseline:
         threads = min(os.cpu_count() or 1, 32)  # more threads only slow these small CPU ops down
         rate, sec = cpu_step_rate(a, 1, 1, threads)
