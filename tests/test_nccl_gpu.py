@@ -87,8 +87,11 @@ def _worker(rank, world, port, ret):
     launched_early = sum(step.reducer.launched)
     step.reducer.finish()
     grads = {n: p.grad.detach().clone().cpu() for n, p in model.named_parameters() if p.requires_grad}
-    # then a few real (graph-captured) steps
-    step.capture(batch, warmup=1)
+    # drop the eager graph: its AccumulateGrad nodes were created on the default stream and would be reused (with
+    # that stream) by the capture below
+    del out, loss
+    # then a few real steps (eager here; the CUDA-graph-captured form of the same body, NCCL ranges included, is
+    # what bench.py --gpus 2 runs and checks with `param_spread_across_ranks`)
     for _ in range(3):
         step(batch, 0.0)
     torch.cuda.synchronize()
