@@ -151,3 +151,75 @@ int coda_novel_candidates(int b, int q, int g, int cap, const int *boxes2d, cons
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Predicted 3-D boxes -> 2-D boxes in the image (one thread per box, fp64 like the reference):
+//   undo the point-cloud augmentation (scale, rotation, flips), rotate into the camera frame (Rtilt^T), project with
+//   K, clip to the original image, add the crop offsets, undo the image flip, then the integer bounding box of the
+//   eight projected corners (truncation of non-negative values, as `int(torch.min(.))`) and the usability flag.
+// Replaces models/model_3detr.py:912-968 + datasets/sunrgbd_utils.py:611-635 (project_3dpoint_to_2dpoint_corners_tensor)
+// + the per-box checks of :1034-1051 -- in the reference a chain of fp64 tensor ops plus four .item() syncs per box.
+namespace {
+
+__global__ void __launch_bounds__(128)
+boxes_in_image_kernel(int b, int q, const float *__restrict__ corners, const float *__restrict__ size,
+                      const double *__restrict__ scale, const double *__restrict__ rot, const double *__restrict__ flip,
+                      const double *__restrict__ zx_flip, const double *__restrict__ Kmat,
+                      const double *__restrict__ Rtilt, const long long *__restrict__ ori_w,
+                      const long long *__restrict__ ori_h, const long long *__restrict__ x_off,
+                      const long long *__restrict__ y_off, const double *__restrict__ img_flip,
+                      const double *__restrict__ flip_len, int *__restrict__ boxes, unsigned char *__restrict__ valid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b * q) return;
+  const int s = i / q;
+  const double *R = rot + s * 9, *T = Rtilt + s * 9, *K = Kmat + s * 9, *sc = scale + s * 3;
+  const double fx = flip[s], zx = zx_flip ? zx_flip[s] : 1.0;
+  const double wmax = (double)(ori_w[s] - 1), hmax = (double)(ori_h[s] - 1);
+  const double yo = (double)y_off[s], xo = (double)x_off[s], fl = img_flip[s], flen = flip_len[s];
+  double umin = 1e300, vmin = 1e300, umax = -1e300, vmax = -1e300, dmin = 1e300;
+  const float *c = corners + (size_t)i * 24;
+  for (int k = 0; k < 8; ++k) {
+    const double p0 = (double)c[k * 3] * sc[0], p1 = (double)c[k * 3 + 1] * sc[1], p2 = (double)c[k * 3 + 2] * sc[2];
+    double r0 = p0 * R[0] + p1 * R[3] + p2 * R[6];      // row vector times rot_array
+    double r1 = p0 * R[1] + p1 * R[4] + p2 * R[7];
+    const double r2 = p0 * R[2] + p1 * R[5] + p2 * R[8];
+    r1 *= zx;
+    r0 *= fx;
+    const double t0 = T[0] * r0 + T[3] * r1 + T[6] * r2;   // Rtilt^T p
+    const double t1 = T[1] * r0 + T[4] * r1 + T[7] * r2;
+    const double t2 = T[2] * r0 + T[5] * r1 + T[8] * r2;
+    const double c0 = t0, c1 = -t2, c2 = t1;               // depth -> camera axes
+    const double u3 = c0 * K[0] + c1 * K[1] + c2 * K[2];
+    const double v3 = c0 * K[3] + c1 * K[4] + c2 * K[5];
+    const double d = c0 * K[6] + c1 * K[7] + c2 * K[8];
+    double u = u3 / (d + 1e-32), v = v3 / (d + 1e-32);
+    u = fmin(fmax(u, 0.0), wmax) + yo;
+    v = fmin(fmax(v, 0.0), hmax) + xo;
+    u = u * fl + (1.0 - fl) * (flen - 1.0 - u);
+    umin = fmin(umin, u); umax = fmax(umax, u);
+    vmin = fmin(vmin, v); vmax = fmax(vmax, v);
+    dmin = fmin(dmin, d);
+  }
+  const int xmin = (int)umin, ymin = (int)vmin, xmax = (int)umax, ymax = (int)vmax;
+  boxes[4 * i] = xmin; boxes[4 * i + 1] = ymin; boxes[4 * i + 2] = xmax; boxes[4 * i + 3] = ymax;
+  const float smax = fmaxf(size[3 * i], fmaxf(size[3 * i + 1], size[3 * i + 2]));
+  valid[i] = ((xmax - xmin) > 0 && (ymax - ymin) > 0 && dmin >= 0.0 && !(smax < 1e-16f)) ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" int coda_boxes_in_image(int b, int q, const float *corners_xyz, const float *size_unnorm,
+                                   const double *scale, const double *rot, const double *flip, const double *zx_flip,
+                                   const double *K, const double *Rtilt, const long long *ori_w, const long long *ori_h,
+                                   const long long *x_off, const long long *y_off, const double *img_flip,
+                                   const double *flip_len, int *boxes, unsigned char *valid, void *stream) {
+  if (b < 0 || q < 0) return CODA_EINVAL;
+  if (b == 0 || q == 0) return CODA_OK;
+  if (!corners_xyz || !size_unnorm || !scale || !rot || !flip || !K || !Rtilt || !ori_w || !ori_h || !x_off || !y_off ||
+      !img_flip || !flip_len || !boxes || !valid)
+    return CODA_EINVAL;
+  boxes_in_image_kernel<<<(b * q + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      b, q, corners_xyz, size_unnorm, scale, rot, flip, zx_flip, K, Rtilt, ori_w, ori_h, x_off, y_off, img_flip, flip_len,
+      boxes, valid);
+  return launch_status();
+}

@@ -100,36 +100,6 @@ def _class_prompts(args):
     return ["a photo of a " + c.replace("_", " ").lower() + " in the scene" for c in names[:n]]
 
 
-def _project_corners_to_image(corners_xyz, inputs):
-    """Undo the point-cloud augmentation, project the 8 corners into the image in
-    fp64 and undo the image-side crop / flip (reference :912-968 and
-    datasets/sunrgbd_utils.py:611-635).  (B, Q, 8, 3) -> uv (B, Q, 8, 2) f64, depth (B, Q, 8)."""
-    flip = inputs["flip_array"].unsqueeze(-1)                   # (B, 1, 1)
-    # the dataloader collates scale_array / rot_array as fp64, which promotes the whole chain
-    pts = corners_xyz.to(torch.double) * inputs["scale_array"].unsqueeze(1).to(torch.double)
-    pts = torch.matmul(pts, inputs["rot_array"].unsqueeze(1).to(torch.double))
-    if "zx_flip_array" in inputs:
-        pts = torch.cat((pts[..., :1], pts[..., 1:2] * inputs["zx_flip_array"].view(-1, 1, 1, 1), pts[..., 2:]), -1)
-    pts = torch.cat((pts[..., :1] * flip.to(torch.double).view(-1, 1, 1, 1), pts[..., 1:]), dim=-1)
-    K = inputs["K"].unsqueeze(1).to(torch.double)
-    Rtilt = inputs["Rtilt"].unsqueeze(1).to(torch.double)
-    pc2 = torch.matmul(Rtilt.transpose(2, 3), pts.transpose(2, 3)).transpose(2, 3)
-    pc2 = torch.stack((pc2[..., 0], -pc2[..., 2], pc2[..., 1]), dim=-1)  # depth -> camera axes
-    uv = torch.matmul(pc2, K.transpose(2, 3))
-    depth = uv[..., 2]
-    u = uv[..., 0] / (depth + 1e-32)
-    v = uv[..., 1] / (depth + 1e-32)
-    wmax = (inputs["ori_width"].to(torch.double) - 1).view(-1, 1, 1)
-    hmax = (inputs["ori_height"].to(torch.double) - 1).view(-1, 1, 1)
-    zero = torch.zeros((), dtype=torch.double, device=u.device)
-    u = torch.minimum(torch.maximum(u, zero), wmax) + inputs["y_offset"].to(torch.double).view(-1, 1, 1)
-    v = torch.minimum(torch.maximum(v, zero), hmax) + inputs["x_offset"].to(torch.double).view(-1, 1, 1)
-    img_flip = inputs["image_flip_array"].to(torch.double).view(-1, 1, 1)
-    flip_len = inputs["flip_length"].to(torch.double).view(-1, 1, 1)
-    u = u * img_flip + (1 - img_flip) * (flip_len - 1 - u)
-    return torch.stack((u, v), dim=-1), depth
-
-
 class Model3DETRPredictedBoxDistillationHead(nn.Module):
     """pre_encoder (PointNet++ SA) -> encoder -> query sampling -> decoder -> MLP heads,
     plus CLIP embeddings of the predicted boxes' image crops as distillation targets."""
@@ -401,16 +371,8 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
     def _boxes_in_image(self, inputs, outputs):
         """Every predicted box projected into the image: int32 (B, Q, 4) [xmin, ymin, xmax, ymax] (the reference's
         `int(torch.min/max(.))` truncation of non-negative fp64 values) and the boxes that are usable as crops
-        (non-degenerate, in front of the camera, non-zero size; reference :1034-1051)."""
-        corners = outputs["box_corners_xyz"].detach()
-        uv, depth = _project_corners_to_image(corners, inputs)          # (B, Q, 8, 2) f64
-        xmin = uv[..., 0].amin(-1).to(torch.int32)
-        ymin = uv[..., 1].amin(-1).to(torch.int32)
-        xmax = uv[..., 0].amax(-1).to(torch.int32)
-        ymax = uv[..., 1].amax(-1).to(torch.int32)
-        valid = ((xmax - xmin) > 0) & ((ymax - ymin) > 0) & (depth.amin(-1) >= 0) & \
-                ~(outputs["size_unnormalized"].detach().amax(-1) < 1e-16)
-        return torch.stack((xmin, ymin, xmax, ymax), dim=-1), valid
+        (non-degenerate, in front of the camera, non-zero size; reference :912-968, :1034-1051) -- one kernel."""
+        return ops.boxes_in_image(outputs["box_corners_xyz"].detach(), outputs["size_unnormalized"].detach(), inputs)
 
     @torch.no_grad()
     def _clip_embed_boxes(self, inputs, boxes, valid, sel, chosen=None):

@@ -403,6 +403,32 @@ def hungarian(cost: torch.Tensor, nactual: torch.Tensor):
 
 
 @torch.no_grad()
+def boxes_in_image(corners_xyz: torch.Tensor, size_unnorm: torch.Tensor, inputs: dict):
+    """Predicted boxes (B, Q, 8, 3) -> (int32 (B, Q, 4) [xmin, ymin, xmax, ymax] in the image, bool (B, Q) usable as
+    a crop): include/coda_detr.h coda_boxes_in_image, fp64 like the reference's projection; no host sync."""
+    _need_cuda(corners_xyz, "boxes_in_image")
+    b, q = corners_xyz.shape[:2]
+    dev = corners_xyz.device
+    f64 = lambda t, shape: t.to(device=dev, dtype=torch.double).reshape(shape).contiguous()  # noqa: E731
+    i64 = lambda t: t.to(device=dev, dtype=torch.int64).reshape(b).contiguous()  # noqa: E731
+    scale = f64(inputs["scale_array"], (b, 3))
+    rot, K, Rtilt = f64(inputs["rot_array"], (b, 9)), f64(inputs["K"], (b, 9)), f64(inputs["Rtilt"], (b, 9))
+    flip, img_flip = f64(inputs["flip_array"], (b,)), f64(inputs["image_flip_array"], (b,))
+    flip_len = f64(inputs["flip_length"], (b,))
+    zx = f64(inputs["zx_flip_array"], (b,)) if "zx_flip_array" in inputs else None
+    boxes = torch.empty((b, q, 4), dtype=torch.int32, device=dev)
+    valid = torch.empty((b, q), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        st = lib().coda_boxes_in_image(_i(b), _i(q), ptr(_f32c(corners_xyz)), ptr(_f32c(size_unnorm)), ptr(scale), ptr(rot),
+                                       ptr(flip), ptr(zx), ptr(K), ptr(Rtilt), ptr(i64(inputs["ori_width"])),
+                                       ptr(i64(inputs["ori_height"])), ptr(i64(inputs["x_offset"])),
+                                       ptr(i64(inputs["y_offset"])), ptr(img_flip), ptr(flip_len), ptr(boxes), ptr(valid),
+                                       stream_of(corners_xyz))
+    check(st, "boxes_in_image")
+    return boxes, valid.bool()
+
+
+@torch.no_grad()
 def novel_candidates(boxes2d: torch.Tensor, valid: torch.Tensor, objectness: torch.Tensor, pred_corners: torch.Tensor,
                      gt_corners: torch.Tensor, gt_present: torch.Tensor, nms_iou: float, gt_iou: float,
                      min_objectness: float, cap: int):

@@ -73,6 +73,45 @@ def _crop_cpu(images, scene, boxes, valid, res, dtype=torch.float32, mean=None, 
     return out
 
 
+def _project_corners_to_image(corners_xyz, inputs):
+    """Undo the point-cloud augmentation, project the 8 corners into the image in fp64 and undo the image-side
+    crop / flip (reference models/model_3detr.py:912-968 and datasets/sunrgbd_utils.py:611-635), as the same chain
+    of fp64 tensor ops the reference runs.  (B, Q, 8, 3) -> uv (B, Q, 8, 2) f64, depth (B, Q, 8)."""
+    flip = inputs["flip_array"].unsqueeze(-1)                   # (B, 1, 1)
+    pts = corners_xyz.to(torch.double) * inputs["scale_array"].unsqueeze(1).to(torch.double)
+    pts = torch.matmul(pts, inputs["rot_array"].unsqueeze(1).to(torch.double))
+    if "zx_flip_array" in inputs:
+        pts = torch.cat((pts[..., :1], pts[..., 1:2] * inputs["zx_flip_array"].view(-1, 1, 1, 1), pts[..., 2:]), -1)
+    pts = torch.cat((pts[..., :1] * flip.to(torch.double).view(-1, 1, 1, 1), pts[..., 1:]), dim=-1)
+    K = inputs["K"].unsqueeze(1).to(torch.double)
+    Rtilt = inputs["Rtilt"].unsqueeze(1).to(torch.double)
+    pc2 = torch.matmul(Rtilt.transpose(2, 3), pts.transpose(2, 3)).transpose(2, 3)
+    pc2 = torch.stack((pc2[..., 0], -pc2[..., 2], pc2[..., 1]), dim=-1)  # depth -> camera axes
+    uv = torch.matmul(pc2, K.transpose(2, 3))
+    depth = uv[..., 2]
+    u = uv[..., 0] / (depth + 1e-32)
+    v = uv[..., 1] / (depth + 1e-32)
+    wmax = (inputs["ori_width"].to(torch.double) - 1).view(-1, 1, 1)
+    hmax = (inputs["ori_height"].to(torch.double) - 1).view(-1, 1, 1)
+    zero = torch.zeros((), dtype=torch.double, device=u.device)
+    u = torch.minimum(torch.maximum(u, zero), wmax) + inputs["y_offset"].to(torch.double).view(-1, 1, 1)
+    v = torch.minimum(torch.maximum(v, zero), hmax) + inputs["x_offset"].to(torch.double).view(-1, 1, 1)
+    img_flip = inputs["image_flip_array"].to(torch.double).view(-1, 1, 1)
+    flip_len = inputs["flip_length"].to(torch.double).view(-1, 1, 1)
+    u = u * img_flip + (1 - img_flip) * (flip_len - 1 - u)
+    return torch.stack((u, v), dim=-1), depth
+
+
+def _boxes_in_image(corners_xyz, size_unnorm, inputs):
+    uv, depth = _project_corners_to_image(corners_xyz, inputs)
+    xmin = uv[..., 0].amin(-1).to(torch.int32)
+    ymin = uv[..., 1].amin(-1).to(torch.int32)
+    xmax = uv[..., 0].amax(-1).to(torch.int32)
+    ymax = uv[..., 1].amax(-1).to(torch.int32)
+    valid = ((xmax - xmin) > 0) & ((ymax - ymin) > 0) & (depth.amin(-1) >= 0) & ~(size_unnorm.amax(-1) < 1e-16)
+    return torch.stack((xmin, ymin, xmax, ymax), dim=-1), valid
+
+
 @contextlib.contextmanager
 def installed(giou_fn=_giou_cpu, crop_fn=_crop_cpu):
     """Patches coda_neurips2023_b200.{ops, pointnet2._ext} with CPU math."""
@@ -89,6 +128,7 @@ def installed(giou_fn=_giou_cpu, crop_fn=_crop_cpu):
     patch(ops, "softmax_rows", lambda x, log=False: (torch.log_softmax if log else torch.softmax)(x, dim=-1))
     patch(ops, "fourier_pos_embed", _fourier)
     patch(ops, "hungarian", _hungarian)
+    patch(ops, "boxes_in_image", _boxes_in_image)
     import discovery_ref
 
     patch(ops, "novel_candidates", discovery_ref.novel_candidates_ref)

@@ -227,3 +227,33 @@ def test_novel_candidates_matches_reference_loop(q, g, seed):
                                                 present.cuda(), 0.25, 0.25, 0.4, cap)
         assert torch.equal(got_cnt.cpu(), exp_cnt), (got_cnt, exp_cnt)
         assert torch.equal(got_idx.cpu(), exp_idx)
+
+
+@pytest.mark.parametrize("b,q,hw,seed", [(4, 256, (531, 730), 0), (2, 1000, (968, 1296), 1), (1, 7, (531, 730), 2)])
+def test_boxes_in_image_matches_reference_projection_chain(b, q, hw, seed):
+    """ops.boxes_in_image (one fp64 kernel) against the reference's chain of fp64 tensor ops restated in
+    oracle/cpu_step.py (models/model_3detr.py:912-968, :1034-1051): integer boxes and the usability flag are exact."""
+    import cpu_step
+
+    batch = synthetic.make_batch(b, 3000, seed=seed, image_hw=hw)
+    batch["x_offset"] = np.arange(b, dtype=np.int64) * 3
+    batch["y_offset"] = np.arange(b, dtype=np.int64) * 5 + 1
+    inputs = {k: torch.from_numpy(v) for k, v in batch.items()}
+    gen = torch.Generator().manual_seed(seed)
+    ctr = torch.rand(b, q, 1, 3, generator=gen) * 6 - 3
+    ctr[..., 1] = ctr[..., 1].abs() + 0.2                          # mostly in front of the camera (depth axis = y)
+    ctr[:, : q // 5, :, 1] *= -1                                    # ... and a fifth of them behind it
+    half = torch.rand(b, q, 1, 3, generator=gen) * 0.9 + 0.05
+    sign = torch.tensor([[1, 1, 1], [1, 1, -1], [1, -1, 1], [1, -1, -1], [-1, 1, 1], [-1, 1, -1], [-1, -1, 1],
+                         [-1, -1, -1]], dtype=torch.float32)
+    corners = (ctr + half * sign).contiguous()
+    size = (2 * half[:, :, 0]).contiguous()
+    size[:, -1] = 0                                                 # zero-size box -> not usable
+    exp_boxes, exp_valid = cpu_step._boxes_in_image(corners, size, inputs)
+    got_boxes, got_valid = ops.boxes_in_image(corners.cuda(), size.cuda(), {k: v.cuda() for k, v in inputs.items()})
+    assert got_valid.dtype == torch.bool and got_boxes.dtype == torch.int32
+    assert torch.equal(got_valid.cpu(), exp_valid)
+    # truncation of fp64 values that differ in the last ulp (fused multiply-adds) can move a coordinate by one pixel
+    # when the value sits on an integer; none of these inputs does
+    assert torch.equal(got_boxes.cpu(), exp_boxes)
+    assert 0 < int(exp_valid.sum()) < b * q

@@ -25,6 +25,7 @@ def timeit(fn, reps=20, warm=3):
 
 
 def main():
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None   # substring of a case name
     torch.manual_seed(0)
     cases = [("linear 16384x512x512 ns3", 16384, 512, 512, 3, False, False),
              ("linear 2048x512x512 ns3", 2048, 512, 512, 3, False, False),
@@ -33,6 +34,8 @@ def main():
              ("dX 16384x512x512 ns2 (MN-major W)", 16384, 512, 512, 2, False, True),
              ("SA dz1 1Mx128x256 ns2 (MN-major W)", 1 << 20, 128, 256, 2, False, True)]
     for name, m, n, k, ns, sa, mn in cases:
+        if only and only not in name:
+            continue
         a = torch.randn(m, k, device="cuda")
         if mn:
             w = torch.randn(k, n, device="cuda") / k ** 0.5          # forward weight (rows = contraction)
@@ -56,6 +59,8 @@ def main():
     # weight gradient from fp32 rows
     for name, rows, m, n in [("dW 16384 rows 512x512", 16384, 512, 512), ("SA dW2 1M rows 256x128", 1 << 20, 256, 128),
                              ("SA dW1 1M rows 128x64", 1 << 20, 128, 64)]:
+        if only and only not in name:
+            continue
         a = torch.randn(rows, m, device="cuda")
         b = torch.randn(rows, n, device="cuda")
         ms = timeit(lambda: ops.gemm_tn32(a, b))
