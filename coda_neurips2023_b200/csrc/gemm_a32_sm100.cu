@@ -14,12 +14,15 @@
 // Epilogue options: bias / ReLU, TMA store of the fp32 tile, and per-column sum / sum-of-squares partials of the
 // OUTPUT (the BatchNorm statistics of the layer just computed: no separate pass over C).
 //
-// Warp roles (384 threads, persistent CTAs, one per SM):
+// Warp roles (512 threads, persistent CTAs, one per SM):
 //   warp 0      TMA producer: raw fp32 A boxes -> raw ring, B plane boxes -> B ring
 //   warp 1      MMA issuer (one elected lane): tcgen05.mma kind::f16, A from TMEM, B from smem descriptors
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue: tcgen05.ld accumulator -> registers -> (stats) -> swizzled staging -> TMA store
-//   warps 8-11  transform: raw ring -> T -> bf16 planes -> TMEM A ring
+//   warps 8-15  transform: raw ring -> T -> bf16 planes -> TMEM A ring.  Two warps share each 32-row TMEM lane
+//               quadrant (warp % 4) and take one half (32 of 64) of the k-block's columns each: the transform is an
+//               instruction-issue-bound stream (load, prologue, split, tcgen05.st) and four warps -- one per
+//               scheduler, nothing to hide its dependent-issue latency behind -- left the tensor pipe waiting
 // C-ABI in include/coda_gemm.h (coda_gemm_a32*).
 #include "../../include/coda_gemm.h"
 #include "sm100_primitives.cuh"
@@ -96,7 +99,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 // RAW_KB: size of the raw-fp32 staging region; it holds RAW_KB / 32 stages (one-input prologues) or RAW_KB / 64
 // (the two-input BatchNorm-backward prologue).
 template <int NSPLIT, int BN, int RAW_KB, int B_STAGES, bool B_MN>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(512, 1)
 gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
   constexpr int MAX_RAW = RAW_KB / 32;
   constexpr int B_TILE = BN * BK * 2;
@@ -156,9 +159,9 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
     prefetch_tmap(&maps.c);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < MAX_RAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
+    for (int s = 0; s < MAX_RAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 8); }
     for (int s = 0; s < B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&a_full[s], 8); mbar_init(&a_empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     mbar_fence_init_cluster();
   }
@@ -261,7 +264,8 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
     }
   } else if (warp >= 8) {
     // ===== transform: raw fp32 rows -> T -> bf16 planes -> TMEM =====
-    const int q = warp - 8;
+    const int q = (warp - 8) & 3;                     // TMEM lane quadrant (a warp reaches lanes 32 * (warp % 4) ...)
+    const int khalf = (warp - 8) >> 2;                // which 32 of the k-block's 64 columns
     const int row = q * 32 + lane;                    // row of the tile == TMEM lane
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int sw = row & 7;
@@ -283,7 +287,8 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
         const uint32_t a_t = tmem_a0 + (uint32_t)as * A_COLS + lane_base;
         const int k0 = kb * BK;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {              // 16 k-elements = 8 TMEM columns per plane
+        for (int c2 = 0; c2 < 2; ++c2) {              // 16 k-elements = 8 TMEM columns per plane
+          const int ch = khalf * 2 + c2;
           float x[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -492,7 +497,7 @@ int launch_a32(const A32Maps &maps, const A32Params &P, cudaStream_t s) {
   // short contraction, many m-tiles: keep the weights of one n-tile resident per CTA
   Q.b_resident = (nkb <= B_STAGES && tiles_n <= num_sms() && tiles_m >= 4 * (num_sms() / tiles_n)) ? 1 : 0;
   if (Q.b_resident) grid = (unsigned)((num_sms() / tiles_n) * tiles_n);
-  kern<<<grid, 384, total, s>>>(maps, Q);
+  kern<<<grid, 512, total, s>>>(maps, Q);
   return launch_status();
 }
 

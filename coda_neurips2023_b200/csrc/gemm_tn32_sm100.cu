@@ -11,7 +11,12 @@
 // memory.  The kernel is a pure stream over R: split-K across all SMs, partial tiles leave through
 // cp.reduce.async.bulk.tensor (.add) into the zero-initialised output.
 //
-// Warp roles (512 threads): 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 4-7 epilogue | 8-15 transform.
+// Warp roles (640 threads): 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 4-19 transform (two rows of each operand
+// slab per warp); warps 4-7 drain the accumulator once the stream has ended.  The transform is an instruction-issue
+// bound stream: with eight warps (two per scheduler) the kernel ran at 0.44 of the HBM roofline with the tensor pipe
+// 25 % busy; sixteen hide the shared-memory and conversion latencies of one another.
+// Optional: the column sums of TA(A) (the bias gradient of the layer whose dW this is) are accumulated by the
+// transform warps on the way -- the values are in registers already -- instead of a separate pass over dY.
 // C-ABI in include/coda_gemm.h (coda_gemm_tn32).
 #include "../../include/coda_gemm.h"
 #include "sm100_primitives.cuh"
@@ -24,6 +29,7 @@ constexpr int BM = 128;      // output rows per tile  (columns of A)
 constexpr int BKR = 32;      // contraction rows per pipeline stage
 constexpr int NS = 2;        // bf16 planes per operand (gradient precision, as the packed TN path)
 constexpr int RAW_STAGES = 3, PL_STAGES = 2;   // fp32 slabs in flight (HBM latency) / converted operand slabs
+constexpr int TW = 16;       // transform warps
 
 struct TN32Maps {
   CUtensorMap a, a2, b, c;
@@ -38,6 +44,7 @@ struct TN32Params {
   const unsigned char *argmax;
   int group;
   const float *b_scale, *b_shift;                       // per column of B (padded)
+  float *a_colsum;           // optional (m): += column sums of TA(A), pre-zeroed by the launcher
   int ksplit;
 };
 
@@ -69,7 +76,7 @@ __device__ __forceinline__ void store_planes4(float4 v, unsigned char *dst, uint
 }
 
 template <int BN>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(640, 1)
 gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
   constexpr int RAW_A = BKR * BM * 4;            // 16 KB: four [32 rows x 32 fp32] SW128 boxes
   constexpr int RAW_B = BKR * BN * 4;
@@ -88,8 +95,10 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
   __shared__ __align__(8) uint64_t pl_full[PL_STAGES], pl_empty[PL_STAGES];
   __shared__ __align__(8) uint64_t acc_full;
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_colsum[BM];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < BM) s_colsum[threadIdx.x] = 0.f;
   const int tiles_n = (P.n + BN - 1) / BN;
   const int tile = blockIdx.x / P.ksplit, ks = blockIdx.x % P.ksplit;
   const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
@@ -106,8 +115,8 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
     if (two_in) prefetch_tmap(&maps.a2);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < RAW_STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 8); }
-    for (int s = 0; s < PL_STAGES; ++s) { mbar_init(&pl_full[s], 8); mbar_init(&pl_empty[s], 1); }
+    for (int s = 0; s < RAW_STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], TW); }
+    for (int s = 0; s < PL_STAGES; ++s) { mbar_init(&pl_full[s], TW); mbar_init(&pl_empty[s], 1); }
     mbar_init(&acc_full, 1);
     mbar_fence_init_cluster();
   }
@@ -177,9 +186,11 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
       }
       __syncwarp();
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 4) {
     // ===== transform: fp32 slabs -> prologue -> two bf16 planes, MN-major swizzled =====
-    const int tw = warp - 8;                         // rows tw, tw + 8, tw + 16, tw + 24 of the slab
+    const int tw = warp - 4;                         // rows tw, tw + 16 of the slab
+    const bool want_colsum = P.a_colsum != nullptr && n0 == 0;
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
     // A: lane = 4-column chunk (128 columns = 32 chunks);  per-column coefficients live in registers
     const int ca = m0 + lane * 4;
     float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), ta = sa, al = sa, be = sa;
@@ -210,8 +221,8 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
       if (P.a_mode == CODA_A32_BN_BWD_POOLED) rem0 = (int)(r0 % P.group);    // the slab's first row within its group
       // ---- A slab
 #pragma unroll
-      for (int j = 0; j < BKR / 8; ++j) {
-        const int r = tw + j * 8;
+      for (int j = 0; j < BKR / TW; ++j) {
+        const int r = tw + j * TW;
         const long long grow = r0 + r;
         const uint32_t roff = (uint32_t)(lane >> 3) * 4096u + (uint32_t)r * 128u + (uint32_t)(((lane & 7) ^ (r & 7)) << 4);
         float4 y = *reinterpret_cast<const float4 *>(raw + roff);
@@ -232,6 +243,7 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
           o.w = ((id.w == gi && fmaf(y.w, sa.w, ta.w) > 0.f) ? sa.w * d.w : 0.f) + fmaf(y.w, al.w, be.w);
         }
         if (grow >= P.rows) o = make_float4(0.f, 0.f, 0.f, 0.f);     // padding rows of the last slab
+        if (want_colsum) { csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w; }
         // destination: box = column / 64, 16-byte chunk = (column % 64) / 8 swizzled by the row, half = (column % 8) / 4
         const int col = lane * 4;
         store_planes4(o, pl + (col >> 6) * (BKR * 128) + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + ((col & 7) >> 2) * 8,
@@ -239,8 +251,8 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
       }
       // ---- B slab
 #pragma unroll
-      for (int j = 0; j < BKR / (8 * B_RPP); ++j) {
-        const int r = (tw + j * 8) * B_RPP + brow_off;
+      for (int j = 0; j < BKR / (TW * B_RPP); ++j) {
+        const int r = (tw + j * TW) * B_RPP + brow_off;
         const long long grow = r0 + r;
         const uint32_t roff = (uint32_t)(bch >> 3) * 4096u + (uint32_t)r * 128u + (uint32_t)(((bch & 7) ^ (r & 7)) << 4);
         float4 v = *reinterpret_cast<const float4 *>(raw + 2 * RAW_A + roff);
@@ -261,8 +273,13 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
         mbar_arrive(&pl_full[ps]);
       }
     }
-  } else if (warp >= 4) {
-    // ===== epilogue: one accumulator per CTA, drained once =====
+    if (want_colsum && a_col_ok) {
+      atomicAdd(&s_colsum[lane * 4], csum.x); atomicAdd(&s_colsum[lane * 4 + 1], csum.y);
+      atomicAdd(&s_colsum[lane * 4 + 2], csum.z); atomicAdd(&s_colsum[lane * 4 + 3], csum.w);
+    }
+  }
+  if (warp >= 4 && warp < 8) {
+    // ===== epilogue: one accumulator per CTA, drained once (the raw ring is idle by then: staging lives there) =====
     const int q = warp - 4;
     unsigned char *stage = epi + (size_t)q * (32 * 128);
     unsigned char *srow = stage + lane * 128;
@@ -294,6 +311,8 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
   }
   tc_fence_before();
   __syncthreads();
+  if (P.a_colsum && n0 == 0 && threadIdx.x < BM && m0 + (int)threadIdx.x < P.m)
+    atomicAdd(P.a_colsum + m0 + threadIdx.x, s_colsum[threadIdx.x]);
   if (warp == 2) tmem_dealloc(tmem_acc, TMEM_COLS);
 }
 
@@ -340,7 +359,11 @@ int launch_tn32(const TN32Maps &maps, TN32Params P, float *c, long long ldc, cud
     cudaError_t e = cudaMemset2DAsync(c, (size_t)ldc * 4, 0, (size_t)P.n * 4, (size_t)P.m, s);
     if (e != cudaSuccess) return (int)e;
   }
-  kern<<<tiles * ksplit, 512, smem, s>>>(maps, P);
+  if (P.a_colsum) {
+    cudaError_t e = cudaMemsetAsync(P.a_colsum, 0, (size_t)P.m * 4, s);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kern<<<tiles * ksplit, 640, smem, s>>>(maps, P);
   return launch_status();
 }
 
@@ -351,7 +374,7 @@ extern "C" {
 int coda_gemm_tn32(long long rows, int m, int n, const float *a, long long lda, int a_mode, const float *a_scale,
                    const float *a_shift, const float *a_alpha, const float *a_beta, const float *a2, long long lda2,
                    const unsigned char *a_argmax, int a_group, const float *b, long long ldb, int b_mode,
-                   const float *b_scale, const float *b_shift, float *c, long long ldc, void *stream) {
+                   const float *b_scale, const float *b_shift, float *c, long long ldc, float *a_colsum, void *stream) {
   if (rows <= 0 || m <= 0 || n <= 0 || !a || !b || !c) return CODA_EINVAL;
   if ((lda & 3) || (ldb & 3) || (ldc & 3) || (m & 3) || (n & 3)) return CODA_EINVAL;
   if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) return CODA_EINVAL;
@@ -378,7 +401,7 @@ int coda_gemm_tn32(long long rows, int m, int n, const float *a, long long lda, 
   TN32Params P;
   P.rows = rows; P.m = m; P.n = n; P.a_mode = a_mode; P.b_mode = b_mode;
   P.a_scale = a_scale; P.a_shift = a_shift; P.a_alpha = a_alpha; P.a_beta = a_beta;
-  P.dpooled = a2; P.argmax = a_argmax; P.group = a_group; P.b_scale = b_scale; P.b_shift = b_shift; P.ksplit = 1;
+  P.dpooled = a2; P.argmax = a_argmax; P.group = a_group; P.b_scale = b_scale; P.b_shift = b_shift; P.a_colsum = a_colsum; P.ksplit = 1;
   cudaStream_t s = (cudaStream_t)stream;
   if (n <= 64) return launch_tn32<64>(maps, P, c, ldc, s);
   return launch_tn32<128>(maps, P, c, ldc, s);

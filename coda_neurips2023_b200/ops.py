@@ -606,10 +606,11 @@ def tn32_ok(a: torch.Tensor) -> bool:
 
 def gemm_tn32(a: torch.Tensor, b: torch.Tensor, *, a_mode: int = A32_PLAIN, a_scale=None, a_shift=None, a_alpha=None,
               a_beta=None, a2=None, argmax=None, group: int = 0, b_mode: int = A32_PLAIN, b_scale=None,
-              b_shift=None, out: torch.Tensor | None = None) -> torch.Tensor:
+              b_shift=None, out: torch.Tensor | None = None, colsum_out: torch.Tensor | None = None) -> torch.Tensor:
     """C (m, n) = sum_r TA(a)[r, :]^T TB(b)[r, :] from the fp32 activations a (R, m), b (R, n) read in place
     (csrc/gemm_tn32_sm100.cu): the weight-gradient GEMM with the BatchNorm-backward / BatchNorm-forward
-    prologues applied inside the kernel.  Two bf16 planes per operand."""
+    prologues applied inside the kernel.  Two bf16 planes per operand.  colsum_out (m,): receives sum_r TA(a)[r, :]
+    (the bias gradient) from the same pass."""
     _need_cuda(a, "gemm_tn32")
     rows, m = a.shape
     n = b.shape[1]
@@ -627,7 +628,7 @@ def gemm_tn32(a: torch.Tensor, b: torch.Tensor, *, a_mode: int = A32_PLAIN, a_sc
         st = lib().coda_gemm_tn32(_ll(rows), _i(m), _i(n), ptr(a), _ll(a.stride(0)), _i(a_mode), ptr(a_scale),
                                   ptr(a_shift), ptr(a_alpha), ptr(a_beta), ptr(a2), _ll(lda2), ptr(argmax), _i(group),
                                   ptr(b), _ll(b.stride(0)), _i(b_mode), ptr(b_scale), ptr(b_shift), ptr(out),
-                                  _ll(out.stride(0)), stream_of(a))
+                                  _ll(out.stride(0)), ptr(colsum_out), stream_of(a))
     check(st, "gemm_tn32")
     return out
 
@@ -748,6 +749,7 @@ class _Linear(torch.autograd.Function):
         m, k = x.shape
         n = weight.shape[0]
         dx = dw = db = None
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[0]:
             if a32_ok(dy):
                 # dX (m, k) = dY (m, n) @ W (n, k): contraction over the ROWS of the forward weight planes
@@ -758,14 +760,21 @@ class _Linear(torch.autograd.Function):
             # dW (n, k) = sum_m dY[m, n] X[m, k]: contraction over the ROWS of both operands
             if tn32_ok(dy) and tn32_ok(x) and nsplit == 2:
                 sw = _sink(weight) if k % 4 == 0 else None
-                dw = gemm_tn32(dy, x, out=sw)    # fp32 rows in place, split inside the kernel
+                sb = None
+                if want_db:      # the bias gradient (column sums of dY) comes out of the same pass
+                    sb = _sink(bias)
+                    db = torch.empty(n, dtype=torch.float32, device=dy.device) if sb is None else sb
+                dw = gemm_tn32(dy, x, out=sw, colsum_out=db)    # fp32 rows in place, split inside the kernel
                 if sw is not None:
                     dw = _sunk(sw)
+                if sb is not None:
+                    db = _sunk(sb)
+                want_db = False
             else:
                 dya = pack_split(dy, m, n, n, 1, nsplit)
                 xa = _packed_rows(x, nsplit)     # shared by every layer that consumed the same x (the six heads)
                 dw = gemm_tn(dya, xa, n, k)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if want_db:
             sb = _sink(bias)
             db = colsum(dy, out=sb)
             if sb is not None:

@@ -116,13 +116,16 @@ int coda_gemm_a32(int nsplit, int m, int n, int k, const float *a, long long lda
  * CODA_A32_AFFINE_RELU (relu(b * b_scale + b_shift): the BatchNorm + ReLU that produced this layer's input).
  * Two bf16 planes per operand (gradient precision).  m, n, lda, ldb, ldc multiples of 4; per-column vectors have
  * at least m (resp. n) entries.  Split-K over all SMs; C is fully overwritten.
+ * a_colsum (m floats, or NULL): overwritten with the column sums of TA(A) -- the bias gradient sum_r dY[r][:]
+ * of the layer (torch.nn.Linear / Conv1d backward), accumulated by the transform warps from the values they already
+ * hold instead of a second pass over dY.
  * Replaces, for dW = dY^T X of every 1x1 conv of the shared MLP (pytorch_utils.py:8-33 backward), the chain
  * "BatchNorm backward -> packed dY planes; packed X planes; packed TN GEMM".
  */
 int coda_gemm_tn32(long long rows, int m, int n, const float *a, long long lda, int a_mode, const float *a_scale,
                    const float *a_shift, const float *a_alpha, const float *a_beta, const float *a2, long long lda2,
                    const unsigned char *a_argmax, int a_group, const float *b, long long ldb, int b_mode,
-                   const float *b_scale, const float *b_shift, float *c, long long ldc, void *stream);
+                   const float *b_scale, const float *b_shift, float *c, long long ldc, float *a_colsum, void *stream);
 
 #ifdef __cplusplus
 }
