@@ -40,9 +40,45 @@ def _row_strided(t: torch.Tensor):
     return None
 
 
-def forward(q, k, v, nhead: int, dropout_p: float = 0.0, salt: int = 0, nsplit: int = 3, half_out: bool = False):
+def mask_bits(mask: torch.Tensor, batch: int):
+    """Boolean / byte attention mask (True = not visible), (Lq, Lk) or (B, Lq, Lk) -> (bits_q, bits_k) for the fused
+    kernels (include/coda_attention.h coda_attention_mask_pack): one 64-bit word per (row, 64-column tile)."""
+    if mask.dim() == 2:
+        mask = mask.unsqueeze(0)
+    assert mask.dim() == 3 and mask.shape[0] in (1, batch), "attn_mask must be (Lq, Lk) or (B, Lq, Lk)"
+    m = mask if mask.dtype == torch.uint8 else mask.to(torch.bool).view(torch.uint8) if mask.dtype == torch.bool \
+        else (mask != 0).view(torch.uint8)
+    _, lq, lk = m.shape
+    sb = m.stride(0) if m.shape[0] == batch and batch > 1 else (0 if m.shape[0] == 1 else m.stride(0))
+    bq = torch.empty((batch, lq, (lk + 63) // 64), dtype=torch.int64, device=m.device)
+    bk = torch.empty((batch, lk, (lq + 63) // 64), dtype=torch.int64, device=m.device)
+    with torch.cuda.device(m.device):
+        st = lib().coda_attention_mask_pack(ctypes.c_int(batch), ctypes.c_int(lq), ctypes.c_int(lk), ptr(m),
+                                            ctypes.c_longlong(sb), ctypes.c_longlong(m.stride(1)),
+                                            ctypes.c_longlong(m.stride(2)), ptr(bq), ptr(bk), stream_of(m))
+    check(st, "attention_mask_pack")
+    return bq, bk
+
+
+def radius_mask_bits(xyz: torch.Tensor, radius: float):
+    """xyz (B, L, 3) fp32 -> bits (B, L, ceil(L/64)) int64 of the mask `cdist(xyz, xyz) >= radius` (reference
+    models/transformer.py:155-162), packed on the device without the (B, L, L) distance matrix; symmetric, so the
+    same tensor is both bits_q and bits_k."""
+    b, l, _ = xyz.shape
+    x = xyz.detach().float().contiguous()
+    bits = torch.empty((b, l, (l + 63) // 64), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        st = lib().coda_attention_mask_radius(ctypes.c_int(b), ctypes.c_int(l), ptr(x), ctypes.c_float(float(radius)),
+                                              ptr(bits), stream_of(x))
+    check(st, "attention_mask_radius")
+    return bits, bits
+
+
+def forward(q, k, v, nhead: int, dropout_p: float = 0.0, salt: int = 0, nsplit: int = 3, half_out: bool = False,
+            mask=None):
     """q (Lq, B, E), k / v (Lk, B, E), fp32 or fp16 (all three alike), each either contiguous or a row-strided
-    slice of a fused projection -> (out (Lq, B, E) fp32, lse (B*H, Lq))."""
+    slice of a fused projection -> (out (Lq, B, E) fp32, lse (B*H, Lq)).  mask: (bits_q, bits_k) from mask_bits /
+    radius_mask_bits, or None."""
     lq, b, e = q.shape
     lk = k.shape[0]
     hd = e // nhead
@@ -67,9 +103,10 @@ def forward(q, k, v, nhead: int, dropout_p: float = 0.0, salt: int = 0, nsplit: 
                                            ctypes.c_float(float(hd) ** -0.5), ptr(q), ptr(k), ptr(v), cl(lds[0]),
                                            cl(lds[1]), cl(lds[2]), ci(1 if is_half else 0), ptr(ws), stream_of(q))
         check(st, "attention_pack")
-        st = L.coda_attention_fwd_packed_ex(ci(b), ci(nhead), ci(lq), ci(lk), ci(hd), ci(nsplit), ptr(ws), ptr(out),
-                                            ci(1 if half_out else 0), ptr(lse), ctypes.c_float(dropout_p),
-                                            ctypes.c_uint(salt & 0xFFFFFFFF), ptr(seed_dev), stream_of(q))
+        st = L.coda_attention_fwd_packed_masked(ci(b), ci(nhead), ci(lq), ci(lk), ci(hd), ci(nsplit), ptr(ws), ptr(out),
+                                                ci(1 if half_out else 0), ptr(lse),
+                                                ptr(None if mask is None else mask[0]), ctypes.c_float(dropout_p),
+                                                ctypes.c_uint(salt & 0xFFFFFFFF), ptr(seed_dev), stream_of(q))
     check(st, "attention_fwd")
     return out, lse
 
@@ -123,22 +160,38 @@ def dropout_mult(bh: int, lq: int, lk: int, dropout_p: float, salt: int, device)
     return out
 
 
-def backward(q, k, v, out, dout, lse, nhead: int, dropout_p: float = 0.0, salt: int = 0):
-    """Fused tcgen05 backward (head dim 64 / 128): returns (dq, dk, dv), each shaped like its input."""
+def backward(q, k, v, out, dout, lse, nhead: int, dropout_p: float = 0.0, salt: int = 0, mask=None, grads=None):
+    """Fused tcgen05 backward (head dim 64 / 128): returns (dq, dk, dv), each shaped like its input.  q / k / v may
+    be row-strided slices of a fused projection (read in place); `grads` = preallocated (dq, dk, dv) views, e.g. the
+    slices of ONE packed gradient buffer of that projection (written in place, nothing to concatenate)."""
     lq, b, e = q.shape
     lk = k.shape[0]
     hd = e // nhead
     assert hd in (64, 128)
-    q, k, v, out, dout = (t.contiguous() for t in (q, k, v, out, dout))
-    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    lds = [_row_strided(t) for t in (q, k, v)]
+    if any(ld is None for ld in lds) or any(t.data_ptr() % 16 for t in (q, k, v)):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        lds = [e, e, e]
+    out, dout = out.contiguous(), dout.contiguous()
+    if grads is None:
+        grads = (torch.empty((lq, b, e), dtype=torch.float32, device=q.device),
+                 torch.empty((lk, b, e), dtype=torch.float32, device=q.device),
+                 torch.empty((lk, b, e), dtype=torch.float32, device=q.device))
+    dq, dk, dv = grads
+    ldg = [_row_strided(t) for t in grads]
+    assert all(ld is not None for ld in ldg) and all(t.data_ptr() % 16 == 0 for t in grads)
+    cl = ctypes.c_longlong
     L = lib()
     L.coda_attention_bwd_workspace_bytes.restype = ctypes.c_longlong
     ws = torch.empty(int(L.coda_attention_bwd_workspace_bytes(b, nhead, lq, lk, hd)), dtype=torch.uint8, device=q.device)
     seed_dev = seed_counter(q.device) if dropout_p > 0.0 else None
     with torch.cuda.device(q.device):
-        st = L.coda_attention_bwd(ctypes.c_int(b), ctypes.c_int(nhead), ctypes.c_int(lq), ctypes.c_int(lk),
-                                  ctypes.c_int(hd), ctypes.c_float(float(hd) ** -0.5), ptr(q), ptr(k), ptr(v), ptr(out),
-                                  ptr(dout), ptr(lse), ptr(dq), ptr(dk), ptr(dv), ctypes.c_float(dropout_p),
-                                  ctypes.c_uint(salt & 0xFFFFFFFF), ptr(seed_dev), ptr(ws), stream_of(q))
+        st = L.coda_attention_bwd_ex(ctypes.c_int(b), ctypes.c_int(nhead), ctypes.c_int(lq), ctypes.c_int(lk),
+                                     ctypes.c_int(hd), ctypes.c_float(float(hd) ** -0.5), ptr(q), ptr(k), ptr(v),
+                                     cl(lds[0]), cl(lds[1]), cl(lds[2]), ptr(out), ptr(dout), ptr(lse), ptr(dq), ptr(dk),
+                                     ptr(dv), cl(ldg[0]), cl(ldg[1]), cl(ldg[2]),
+                                     ptr(None if mask is None else mask[0]), ptr(None if mask is None else mask[1]),
+                                     ctypes.c_float(dropout_p), ctypes.c_uint(salt & 0xFFFFFFFF), ptr(seed_dev), ptr(ws),
+                                     stream_of(q))
     check(st, "attention_bwd")
     return dq, dk, dv

@@ -43,6 +43,50 @@ dropout_mult_kernel(long long total, int lq, int lk, uint32_t seed, const uint32
   mult[i] = drop_keep(seed, bh, q, k, thresh32) ? keep_scale : 0.f;
 }
 
+// Attention masks travel bit-packed: bits[b][row][tile] (one 64-bit word per 64 columns), bit c set = column
+// 64 * tile + c is NOT visible from that row (torch's boolean attn_mask convention).  The forward and the dQ kernel
+// index rows by query, the dK/dV kernel by key (the transposed packing), so every softmax thread reads one word
+// per tile.  rows / cols and the strides are in the orientation being packed.
+__global__ void __launch_bounds__(128)
+mask_pack_kernel(int B, int rows, int cols, const unsigned char *__restrict__ mask, long long stride_b,
+                 long long stride_r, long long stride_c, unsigned long long *__restrict__ bits) {
+  const int nt = (cols + 63) / 64;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * rows * nt) return;
+  const int t = (int)(i % nt);
+  const long long br = i / nt;
+  const int r = (int)(br % rows), b = (int)(br / rows);
+  const unsigned char *src = mask + (size_t)b * stride_b + (size_t)r * stride_r;
+  unsigned long long w = 0;
+  for (int c = 0; c < 64; ++c) {
+    const int col = t * 64 + c;
+    if (col < cols && __ldg(src + (size_t)col * stride_c)) w |= 1ull << c;
+  }
+  bits[i] = w;
+}
+
+// Radius mask of the reference's MaskedTransformerEncoder (models/transformer.py:155-162): point j is masked for
+// point i when |x_i - x_j| >= radius (Euclidean, as torch.cdist).  Symmetric: one packing serves both orientations.
+__global__ void __launch_bounds__(128)
+mask_radius_kernel(int B, int L, const float *__restrict__ xyz, float radius, unsigned long long *__restrict__ bits) {
+  const int nt = (L + 63) / 64;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * L * nt) return;
+  const int t = (int)(i % nt);
+  const long long br = i / nt;
+  const int r = (int)(br % L), b = (int)(br / L);
+  const float *base = xyz + (size_t)b * L * 3;
+  const float x = __ldg(base + 3 * r), y = __ldg(base + 3 * r + 1), z = __ldg(base + 3 * r + 2);
+  unsigned long long w = 0;
+  for (int c = 0; c < 64; ++c) {
+    const int col = t * 64 + c;
+    if (col >= L) break;
+    const float dx = x - __ldg(base + 3 * col), dy = y - __ldg(base + 3 * col + 1), dz = z - __ldg(base + 3 * col + 2);
+    if (sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) >= radius) w |= 1ull << c;
+  }
+  bits[i] = w;
+}
+
 // ------------------------------------------------------------------ the kernel
 struct AttnMaps {
   CUtensorMap k[3], v[3];
@@ -107,7 +151,7 @@ template <int HD, int NSPLIT, bool ONE_TILE>
 __global__ void __launch_bounds__(AttnCfg<HD, NSPLIT, ONE_TILE>::THREADS, AttnCfg<HD, NSPLIT, ONE_TILE>::MIN_CTAS)
 attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__restrict__ qplanes, int Lq, int Lk,
                 int B, int H, float *__restrict__ out, float *__restrict__ lse, float drop_p, uint32_t seed,
-                const uint32_t *__restrict__ seed_dev, int out_half) {
+                const uint32_t *__restrict__ seed_dev, int out_half, const unsigned long long *__restrict__ mask_q) {
   using SM = AttnCfg<HD, NSPLIT, ONE_TILE>;
   if (seed_dev) seed += __ldg(seed_dev);  // per-step counter kept on the device (CUDA-graph friendly)
   constexpr int KB = SM::KB, NWG = SM::NWG, NP = SM::NP, NST = SM::NST;
@@ -273,6 +317,9 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
     const uint32_t lcg_a4 = jump.a[3], lcg_c4 = jump.c[3];
     const uint32_t my_o = tmem_o + (uint32_t)g * HD + lane_base;
     const uint32_t my_p = tmem_p + (uint32_t)(g * SM::P_COLS) + lane_base;
+    // attention mask: one 64-bit word per (batch, query row, key tile), bit c set = key c of the tile is not visible
+    const unsigned long long *mrow =
+        mask_q ? mask_q + ((size_t)(bh / H) * Lq + (q0 + row < Lq ? q0 + row : 0)) * (size_t)ntiles : nullptr;
 
     for (int j = g; j < ntiles; j += NWG) {
       const uint32_t ph = (uint32_t)(j / NWG) & 1u;
@@ -290,10 +337,21 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
         for (int c = 0; c < 64; ++c)
           if (c >= kvalid) sr[c >> 5][c & 31] = __float_as_uint(-INFINITY);
       }
+      if (mrow) {
+        const unsigned long long mb = __ldg(mrow + j);
+        const uint32_t mlo = (uint32_t)mb, mhi = (uint32_t)(mb >> 32);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if ((mlo >> c) & 1u) sr[0][c] = __float_as_uint(-INFINITY);
+          if ((mhi >> c) & 1u) sr[1][c] = __float_as_uint(-INFINITY);
+        }
+      }
       float mloc = __uint_as_float(sr[0][0]);
 #pragma unroll
       for (int c = 1; c < 64; ++c) mloc = fmaxf(mloc, __uint_as_float(sr[c >> 5][c & 31]));
-      const float m_new = fmaxf(m_run, mloc);
+      const float m_run_new = fmaxf(m_run, mloc);
+      // a row whose keys so far are all masked keeps m = -inf; exponentials are then taken against 0 (all zero)
+      const float m_new = m_run_new == -INFINITY ? 0.f : m_run_new;
       const float alpha = ex2_approx(m_run - m_new);  // m_run = -inf on the first tile -> 0
       float lsum = 0.f;
       uint32_t dx[4] = {0, 0, 0, 0};
@@ -333,7 +391,7 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
         for (int pl = 0; pl < NP; ++pl) tmem_st_32x8(my_p + (uint32_t)(pl * (KT / 2) + ch * 8), w[pl]);
       }
       l_run = l_run * alpha + lsum;
-      m_run = m_new;
+      m_run = m_run_new;
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[g]);
@@ -399,12 +457,13 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (g == 0) {
         const float m1 = merge_ml[row][0], l1 = merge_ml[row][1];
-        const float m = fmaxf(m_run, m1);            // warpgroup 0 owns tile 0: m_run is finite
+        const float mm = fmaxf(m_run, m1);           // -inf only if every key of the row is masked
+        const float m = mm == -INFINITY ? 0.f : mm;
         const float a0 = ex2_approx(m_run - m), a1 = ex2_approx(m1 - m);
 #pragma unroll
         for (int d = 0; d < HD; ++d) o_acc[d] = o_acc[d] * a0 + scratch[d * QT + row] * a1;
         l_run = l_run * a0 + l1 * a1;
-        m_run = m;
+        m_run = mm;
       }
     }
     // ===== epilogue: normalise, store (Lq, B, H*HD) and the log-sum-exp (natural-log units) =====
@@ -427,7 +486,8 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
 
 template <int HD, int NSPLIT, bool ONE_TILE = false>
 int launch_attn(const AttnMaps &maps, const __nv_bfloat16 *qplanes, int Lq, int Lk, int B, int H, float *out,
-                float *lse, float drop_p, uint32_t seed, const uint32_t *seed_dev, cudaStream_t s, int out_half = 0) {
+                float *lse, float drop_p, uint32_t seed, const uint32_t *seed_dev, cudaStream_t s, int out_half = 0,
+                const unsigned long long *mask_q = nullptr) {
   if (out_half && !ONE_TILE) return CODA_EINVAL;   // fp16 output exists on the single-tile (CLIP tower) instance
   using SM = AttnCfg<HD, NSPLIT, ONE_TILE>;
   constexpr size_t smem = SM::TOTAL + 1024;
@@ -439,7 +499,7 @@ int launch_attn(const AttnMaps &maps, const __nv_bfloat16 *qplanes, int Lq, int 
     configured = true;
   }
   const dim3 grid((Lq + QT - 1) / QT, B * H);
-  kern<<<grid, SM::THREADS, smem, s>>>(maps, qplanes, Lq, Lk, B, H, out, lse, drop_p, seed, seed_dev, out_half);
+  kern<<<grid, SM::THREADS, smem, s>>>(maps, qplanes, Lq, Lk, B, H, out, lse, drop_p, seed, seed_dev, out_half, mask_q);
   return launch_status();
 }
 
@@ -503,6 +563,13 @@ int coda_attention_fwd_packed(int b, int h, int lq, int lk, int hd, int nsplit, 
 int coda_attention_fwd_packed_ex(int b, int h, int lq, int lk, int hd, int nsplit, const void *workspace,
                                  void *out_v, int out_half, float *lse, float dropout_p, unsigned int seed,
                                  const unsigned int *seed_dev, void *stream) {
+  return coda_attention_fwd_packed_masked(b, h, lq, lk, hd, nsplit, workspace, out_v, out_half, lse, nullptr, dropout_p,
+                                          seed, seed_dev, stream);
+}
+
+int coda_attention_fwd_packed_masked(int b, int h, int lq, int lk, int hd, int nsplit, const void *workspace,
+                                     void *out_v, int out_half, float *lse, const unsigned long long *mask_q,
+                                     float dropout_p, unsigned int seed, const unsigned int *seed_dev, void *stream) {
   float *out = reinterpret_cast<float *>(out_v);
   int st = attn_check(b, h, lq, lk, hd, nsplit);
   if (st != CODA_OK) return st;
@@ -520,8 +587,9 @@ int coda_attention_fwd_packed_ex(int b, int h, int lq, int lk, int hd, int nspli
     st = make_tmap_k_major_16b(&maps.v[p], vp + (size_t)p * bh * lk * hd, 0, hd, lk, bh, hd, (long long)lk * hd, KT);
     if (st != CODA_OK) return st;
   }
-#define CODA_ATTN(HD_, NS) return launch_attn<HD_, NS>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s)
-  if (hd == 64 && lk <= KT && nsplit <= 2) {   // single key tile (CLIP image tower): two CTAs per SM
+#define CODA_ATTN(HD_, NS) \
+  return launch_attn<HD_, NS>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s, 0, mask_q)
+  if (hd == 64 && lk <= KT && nsplit <= 2 && !mask_q) {   // single key tile (CLIP image tower): two CTAs per SM
     if (nsplit == 1) return launch_attn<64, 1, true>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s, out_half);
     return launch_attn<64, 2, true>(maps, qp, lq, lk, b, h, out, lse, dropout_p, seed, seed_dev, s, out_half);
   }
@@ -535,6 +603,27 @@ int coda_attention_fwd_packed_ex(int b, int h, int lq, int lk, int hd, int nspli
   if (nsplit == 2) CODA_ATTN(128, 2);
   CODA_ATTN(128, 3);
 #undef CODA_ATTN
+}
+
+int coda_attention_mask_pack(int b, int lq, int lk, const unsigned char *mask, long long stride_b, long long stride_q,
+                             long long stride_k, unsigned long long *bits_q, unsigned long long *bits_k, void *stream) {
+  if (b < 0 || lq <= 0 || lk <= 0) return CODA_EINVAL;
+  if (b == 0) return CODA_OK;
+  if (!mask || !bits_q || !bits_k) return CODA_EINVAL;
+  const long long nq = (long long)b * lq * ((lk + 63) / 64), nk = (long long)b * lk * ((lq + 63) / 64);
+  cudaStream_t s = (cudaStream_t)stream;
+  mask_pack_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, s>>>(b, lq, lk, mask, stride_b, stride_q, stride_k, bits_q);
+  mask_pack_kernel<<<(unsigned)((nk + 127) / 128), 128, 0, s>>>(b, lk, lq, mask, stride_b, stride_k, stride_q, bits_k);
+  return launch_status();
+}
+
+int coda_attention_mask_radius(int b, int l, const float *xyz, float radius, unsigned long long *bits, void *stream) {
+  if (b < 0 || l <= 0) return CODA_EINVAL;
+  if (b == 0) return CODA_OK;
+  if (!xyz || !bits) return CODA_EINVAL;
+  const long long n = (long long)b * l * ((l + 63) / 64);
+  mask_radius_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(b, l, xyz, radius, bits);
+  return launch_status();
 }
 
 int coda_attention_dropout_mult(int bh, int lq, int lk, float dropout_p, unsigned int seed,

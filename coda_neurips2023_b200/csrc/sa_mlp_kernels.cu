@@ -197,6 +197,46 @@ bn_stats_finalize_affine_kernel(int nblocks, long long rows, int c, int cpad,
     shift[ch] = beta[ch] - (float)m * sc;
   }
 }
+// ---- synchronised BatchNorm (statistics over the batches of ALL ranks, reference main.py:993 convert_sync_batchnorm)
+// Stage 1 on each rank: the per-channel column sums as fp64 [sum(c) | sum of squares(c)] -- what the ranks
+// all-reduce (fp64: E[x^2] - E[x]^2 from fp32 sums would cancel catastrophically for |mean| >> std).
+__global__ void __launch_bounds__(256)
+bn_sums_f64_kernel(int nblocks, int c, const float *__restrict__ partial, double *__restrict__ sums) {
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (ch >= c) return;
+  double s, q;
+  warp_partials_sum(nblocks, c, ch, partial, s, q);
+  if ((threadIdx.x & 31) != 0) return;
+  sums[ch] = s;
+  sums[c + ch] = q;
+}
+// Stage 2 (after the all-reduce): statistics over `rows` = the global row count, running buffers, folded affine map
+__global__ void __launch_bounds__(256)
+bn_finalize_sums_kernel(long long rows, int c, int cpad, const double *__restrict__ sums, float eps, float momentum,
+                        float *running_mean, float *running_var, const float *__restrict__ gamma,
+                        const float *__restrict__ beta, float *__restrict__ mean, float *__restrict__ invstd,
+                        float *__restrict__ scale, float *__restrict__ shift) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= cpad) return;
+  if (ch >= c) {
+    if (scale) { scale[ch] = 0.f; shift[ch] = 0.f; }
+    return;
+  }
+  const double n = (double)rows, m = sums[ch] / n;
+  double var = sums[c + ch] / n - m * m;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)eps));
+  mean[ch] = (float)m;
+  invstd[ch] = is;
+  if (running_mean) running_mean[ch] = (1.0f - momentum) * running_mean[ch] + momentum * (float)m;
+  if (running_var) running_var[ch] = (1.0f - momentum) * running_var[ch] + momentum * (float)(var * (n / fmax(n - 1.0, 1.0)));
+  if (scale) {
+    const float sc = gamma[ch] * is;
+    scale[ch] = sc;
+    shift[ch] = beta[ch] - (float)m * sc;
+  }
+}
+
 // BatchNorm-backward coefficients of the GEMM prologue: dy = [z > 0] * scale * d + alpha * y + beta
 //   alpha = -scale * invstd * s2 / N,   beta = -scale * s1 / N - alpha * mean
 __global__ void bn_bwd_coefs_kernel(int c, int cpad, long long rows, const float *__restrict__ mean,
@@ -512,6 +552,32 @@ int coda_bn_stats_finalize(int nblocks, long long rows, int c, const float *part
   const int cpad = (c + 63) / 64 * 64;
   bn_stats_finalize_affine_kernel<<<(cpad + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
       nblocks, rows, c, cpad, partial, eps, momentum, running_mean, running_var, gamma, beta, mean, invstd, scale, shift);
+  return coda::launch_status();
+}
+
+int coda_bn_rows_sums(long long rows, int c, const float *y, double *sums, float *scratch, void *stream) {
+  if (rows <= 0 || !channels_ok(c) || !y || !sums || !scratch) return CODA_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = grid_for(rows, c);
+  bn_stats_partial_kernel<<<grid, THREADS, 0, s>>>(rows, c, y, scratch);
+  bn_sums_f64_kernel<<<(c + 7) / 8, 256, 0, s>>>((int)grid, c, scratch, sums);
+  return coda::launch_status();
+}
+
+int coda_bn_partials_sums(int nblocks, int c, const float *partial, double *sums, void *stream) {
+  if (nblocks <= 0 || c <= 0 || !partial || !sums) return CODA_EINVAL;
+  bn_sums_f64_kernel<<<(c + 7) / 8, 256, 0, (cudaStream_t)stream>>>(nblocks, c, partial, sums);
+  return coda::launch_status();
+}
+
+int coda_bn_stats_finalize_sums(long long rows, int c, const double *sums, float eps, float momentum,
+                                float *running_mean, float *running_var, const float *gamma, const float *beta,
+                                float *mean, float *invstd, float *scale, float *shift, void *stream) {
+  if (rows <= 0 || c <= 0 || !sums || !mean || !invstd) return CODA_EINVAL;
+  if ((scale != nullptr) != (shift != nullptr) || (scale && (!gamma || !beta))) return CODA_EINVAL;
+  const int cpad = scale ? (c + 63) / 64 * 64 : c;
+  bn_finalize_sums_kernel<<<(cpad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      rows, c, cpad, sums, eps, momentum, running_mean, running_var, gamma, beta, mean, invstd, scale, shift);
   return coda::launch_status();
 }
 

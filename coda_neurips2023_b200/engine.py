@@ -278,9 +278,15 @@ class TrainStep:
     state is broadcast, the optimizer is built.  The probe and the graph warm-up leave NO trace: parameters,
     optimizer state, BatchNorm buffers and the dropout counter are restored afterwards."""
 
-    def __init__(self, args, model, criterion, device, nbuckets: int = 4):
+    def __init__(self, args, model, criterion, device, nbuckets: int = 4, sync_bn: bool | None = None):
+        """sync_bn: synchronise BatchNorm statistics over the ranks (the reference converts to SyncBatchNorm when
+        ngpus > 1, main.py:993).  Default (None -> args.sync_bn, else False): per-GPU statistics and exactly one
+        gradient all-reduce per step, as the north-star asks; True adds one small all-reduce per BatchNorm layer
+        and direction and makes N ranks x B scenes equal one rank x N*B scenes."""
         self.args, self.model, self.criterion, self.device = args, model, criterion, device
         self.world = get_world_size()
+        self.sync_bn = bool(getattr(args, "sync_bn", False) if sync_bn is None else sync_bn)
+        ops.set_bn_sync(self.sync_bn and self.world > 1)
         self.nbuckets = nbuckets
         self.lr = torch.tensor(float(args.base_lr), device=device)
         self.flat = None

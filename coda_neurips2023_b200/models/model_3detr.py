@@ -35,7 +35,7 @@ from ..pointnet2.pointnet2_utils import furthest_point_sample
 from ..utils.pc_util import scale_points, shift_scale_points
 from .helpers import GenericMLP
 from .position_embedding import PositionEmbeddingCoordsSine
-from .transformer import (TransformerDecoder, TransformerDecoderLayer, TransformerEncoder,
+from .transformer import (MaskedTransformerEncoder, TransformerDecoder, TransformerDecoderLayer, TransformerEncoder,
                           TransformerEncoderLayer)
 
 CLIP_CHECKPOINT = "./CLIP/pretrain_models/ViT-B-16.pt"  # path the reference hard-codes (:325)
@@ -578,7 +578,15 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
                 if_cmp_class=False):
         point_clouds = inputs["point_clouds"]
         enc_xyz, enc_features, enc_inds = self.run_encoder(point_clouds)
-        enc_features = self.encoder_to_decoder_projection(enc_features.permute(1, 2, 0)).permute(2, 0, 1)
+        proj = self.encoder_to_decoder_projection
+        if isinstance(proj.layers[0], nn.Conv1d) and enc_features.is_contiguous():
+            # 1x1 convolutions + BatchNorm over (batch, position) do not care about the order of the rows: run the
+            # stack on the (position, batch) rows as they lie in memory -- the reference's (B, C, N) round trip
+            # (:1774) would cost a transposed copy in and a strided, re-copied memory tensor out
+            npos, bsz, _ = enc_features.shape
+            enc_features = proj.forward_rows(enc_features.reshape(npos * bsz, -1)).view(npos, bsz, -1)
+        else:
+            enc_features = proj(enc_features.permute(1, 2, 0)).permute(2, 0, 1)
         if encoder_only:
             return enc_xyz, enc_features.transpose(0, 1)
         point_cloud_dims = [inputs["point_cloud_dims_min"], inputs["point_cloud_dims_max"]]
@@ -618,12 +626,18 @@ def build_preencoder(args):
 
 
 def build_encoder(args):
-    if args.enc_type != "vanilla":
-        raise NotImplementedError(f"enc_type={args.enc_type}: only the vanilla encoder (every shipped CoDA "
-                                  "script) is on the B200 path; the masked encoder needs attention masks")
+    # reference models/model_3detr.py:3946-3984
     layer = TransformerEncoderLayer(d_model=args.enc_dim, nhead=args.enc_nhead, dim_feedforward=args.enc_ffn_dim,
                                     dropout=args.enc_dropout, activation=args.enc_activation)
-    return TransformerEncoder(encoder_layer=layer, num_layers=args.enc_nlayers)
+    if args.enc_type == "vanilla":
+        return TransformerEncoder(encoder_layer=layer, num_layers=args.enc_nlayers)
+    if args.enc_type == "masked":
+        interim_downsampling = PointnetSAModuleVotes(radius=0.4, nsample=32, npoint=args.preenc_npoints // 2,
+                                                     mlp=[args.enc_dim, 256, 256, args.enc_dim], normalize_xyz=True)
+        masking_radius = [math.pow(x, 2) for x in [0.4, 0.8, 1.2]]
+        return MaskedTransformerEncoder(encoder_layer=layer, num_layers=3, interim_downsampling=interim_downsampling,
+                                        masking_radius=masking_radius)
+    raise ValueError(f"Unknown encoder type {args.enc_type}")
 
 
 def build_decoder(args):

@@ -27,6 +27,11 @@ class MultiheadAttention(nn.Module):
     forward(query, key, value, attn_mask=None, key_padding_mask=None) -> (out, None);
     attention weights are not returned (the reference discards them everywhere
     except under `return_attn_weights`, which no shipped configuration sets).
+
+    attn_mask: boolean (True = not visible), (Lq, Lk), (B, Lq, Lk) or the head-tiled (B*H, Lq, Lk) the reference's
+    MaskedTransformerEncoder builds (every head carries the same mask: the first of each H is used) -- or the packed
+    (bits_q, bits_k) pair of ops.attention_mask_bits / ops.radius_mask_bits, which skips the dense mask entirely.
+    key_padding_mask (B, Lk) is folded into the same packed mask.
     """
 
     def __init__(self, embed_dim: int, num_heads: int, dropout: float = 0.0):
@@ -46,21 +51,44 @@ class MultiheadAttention(nn.Module):
 
     def forward(self, query: Tensor, key: Tensor, value: Tensor, attn_mask: Optional[Tensor] = None,
                 key_padding_mask: Optional[Tensor] = None, need_weights: bool = False):
-        if attn_mask is not None or key_padding_mask is not None:
-            raise NotImplementedError("masked attention (enc_type=masked) is not on the B200 hot path yet")
         e = self.embed_dim
         w, b = self.in_proj_weight, self.in_proj_bias
-        if query is key and key is value:      # encoder self-attention: one packed GEMM
-            q, k, v = ops.linear(query, w, b).split(e, dim=-1)
-        elif query is key:                      # decoder self-attention: q = k = tgt + pos, v = tgt
-            q, k = ops.linear(query, w[: 2 * e], b[: 2 * e]).split(e, dim=-1)
-            v = ops.linear(value, w[2 * e:], b[2 * e:])
+        mask = self._packed_mask(attn_mask, key_padding_mask, query.shape[1], query.shape[0], key.shape[0])
+        if query is key and key is value:      # encoder self-attention: ONE fused q|k|v GEMM, consumed in place
+            out = ops.attention_fused(ops.linear(query, w, b), None, "qkv", self.num_heads, self.dropout,
+                                      self.training, mask)
+        elif query is key:                      # decoder self-attention: q = k = tgt + pos (fused q|k GEMM), v = tgt
+            out = ops.attention_fused(ops.linear(query, w[: 2 * e], b[: 2 * e]), ops.linear(value, w[2 * e:], b[2 * e:]),
+                                      "qk_v", self.num_heads, self.dropout, self.training, mask)
         else:                                   # cross-attention
             q = ops.linear(query, w[:e], b[:e])
             k = ops.linear(key, w[e: 2 * e], b[e: 2 * e])
             v = ops.linear(value, w[2 * e:], b[2 * e:])
-        out = ops.attention(q, k, v, self.num_heads, self.dropout, self.training)
+            out = ops.attention(q, k, v, self.num_heads, self.dropout, self.training, mask=mask)
         return self.out_proj(out), None
+
+    def _packed_mask(self, attn_mask, key_padding_mask, batch, lq, lk):
+        if attn_mask is None and key_padding_mask is None:
+            return None
+        if isinstance(attn_mask, tuple):          # already packed
+            if key_padding_mask is not None:
+                raise NotImplementedError("key_padding_mask together with a pre-packed attn_mask")
+            return attn_mask
+        m = None
+        if attn_mask is not None:
+            if attn_mask.dtype != torch.bool:
+                if attn_mask.is_floating_point():
+                    raise NotImplementedError("additive float attention masks: pass a boolean mask")
+                attn_mask = attn_mask != 0
+            m = attn_mask
+            if m.dim() == 3 and m.shape[0] == batch * self.num_heads and self.num_heads > 1:
+                m = m[:: self.num_heads]         # head-tiled copy of a per-scene mask (reference transformer.py:190-194)
+            if m.dim() == 2:
+                m = m.unsqueeze(0)
+        if key_padding_mask is not None:
+            kp = key_padding_mask.to(torch.bool).view(batch, 1, lk)
+            m = kp.expand(batch, lq, lk) if m is None else (m | kp)
+        return ops.attention_mask_bits(m, batch)
 
 
 class TransformerEncoder(nn.Module):
@@ -86,15 +114,62 @@ class TransformerEncoder(nn.Module):
             if pos is not None:
                 pos = pos.flatten(2).permute(2, 0, 1)
         output = src
-        if mask is not None:
-            raise NotImplementedError("attention masks are not supported by the fused attention kernel")
         for layer in self.layers:
-            output = layer(output, src_mask=None, src_key_padding_mask=src_key_padding_mask, pos=pos)
+            output = layer(output, src_mask=mask, src_key_padding_mask=src_key_padding_mask, pos=pos)
         if self.norm is not None:
             output = self.norm(output)
         if transpose_swap:
             output = output.permute(1, 2, 0).view(bs, c, h, w).contiguous()
         return xyz, output, None
+
+
+class MaskedTransformerEncoder(TransformerEncoder):
+    """`--enc_type masked` (reference models/transformer.py:146-211): layer l only attends within
+    `masking_radius[l]` of each point; after the first layer the points are down-sampled by a set-abstraction
+    module.  The radius mask is built bit-packed on the device straight from the coordinates (no (B, N, N) distance
+    matrix, no head-tiled copy) and applied inside the fused attention kernels, forward and backward."""
+
+    def __init__(self, encoder_layer, num_layers, masking_radius, interim_downsampling, norm=None,
+                 weight_init_name="xavier_uniform"):
+        super().__init__(encoder_layer, num_layers, norm=norm, weight_init_name=weight_init_name)
+        assert len(masking_radius) == num_layers
+        self.masking_radius = masking_radius
+        self.interim_downsampling = interim_downsampling
+
+    def compute_mask(self, xyz, radius, dist=None):
+        """The reference's dense form (boolean (B, N, N), True = outside the radius) -- kept for callers / tests; the
+        forward below uses the packed form."""
+        with torch.no_grad():
+            if dist is None or dist.shape[1] != xyz.shape[1]:
+                dist = torch.cdist(xyz, xyz, p=2)
+            return dist >= radius, dist
+
+    def forward(self, src, mask: Optional[Tensor] = None, src_key_padding_mask: Optional[Tensor] = None,
+                pos: Optional[Tensor] = None, xyz: Optional[Tensor] = None, transpose_swap: Optional[bool] = False):
+        if transpose_swap:
+            bs, c, h, w = src.shape
+            src = src.flatten(2).permute(2, 0, 1)
+            if pos is not None:
+                pos = pos.flatten(2).permute(2, 0, 1)
+        output = src
+        xyz_inds = None
+        for idx, layer in enumerate(self.layers):
+            lmask = None
+            if self.masking_radius[idx] > 0:
+                lmask = ops.radius_mask_bits(xyz, self.masking_radius[idx])
+            output = layer(output, src_mask=lmask, src_key_padding_mask=src_key_padding_mask, pos=pos)
+            if idx == 0 and self.interim_downsampling:
+                # (npoints, batch, channel) -> (batch, channel, npoints) for the set-abstraction module and back
+                xyz, output, xyz_inds = self.interim_downsampling(xyz, output.permute(1, 2, 0).contiguous())
+                output = output.permute(2, 0, 1)
+        if self.norm is not None:
+            output = self.norm(output)
+        if transpose_swap:
+            output = output.permute(1, 2, 0).view(bs, c, h, w).contiguous()
+        return xyz, output, xyz_inds
+
+    def extra_repr(self):
+        return "masking_radius=" + ", ".join("%.2f" % x for x in self.masking_radius)
 
 
 class TransformerEncoderLayer(nn.Module):

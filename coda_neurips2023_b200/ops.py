@@ -253,6 +253,68 @@ def bn_channels_ok(c: int) -> bool:
     return 4 <= c <= 1024 and c % 4 == 0 and 256 % (c // 4) == 0
 
 
+# ---- synchronised BatchNorm (reference main.py:993 convert_sync_batchnorm): an OPTION of this package -- the default
+# is per-GPU statistics and exactly one gradient all-reduce per step.  When on, every BatchNorm
+# executed by bn_act_rows / sa_mlp takes its batch statistics over all ranks: one 16*C-byte fp64 all-reduce per layer
+# forward, one 8*C-byte fp32 all-reduce backward.  Equal row counts per rank (fixed batch per GPU) are assumed.
+_BN_SYNC = {"on": False, "group": None}
+
+
+def set_bn_sync(enabled: bool, group=None) -> None:
+    _BN_SYNC["on"], _BN_SYNC["group"] = bool(enabled), group
+
+
+def bn_sync_world() -> int:
+    import torch.distributed as dist
+
+    if not _BN_SYNC["on"] or not dist.is_available() or not dist.is_initialized():
+        return 1
+    return dist.get_world_size(_BN_SYNC["group"])
+
+
+def bn_stats_synced(rows: int, c: int, bn, momentum: float, track: bool, gamma, beta, want_affine: bool, *, y=None,
+                    partials=None):
+    """Global batch statistics: local fp64 column sums (from y, or from a GEMM epilogue's partials) -> all-reduce ->
+    finalize over rows * world.  Returns (mean, invstd, scale | None, shift | None)."""
+    import torch.distributed as dist
+
+    src = y if y is not None else partials
+    dev = src.device
+    world = bn_sync_world()
+    sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
+    mean = torch.empty(c, dtype=torch.float32, device=dev)
+    invstd = torch.empty(c, dtype=torch.float32, device=dev)
+    scale = shift = None
+    if want_affine:
+        scale = torch.empty(_pad64(c), dtype=torch.float32, device=dev)
+        shift = torch.empty(_pad64(c), dtype=torch.float32, device=dev)
+    L = lib()
+    with torch.cuda.device(dev):
+        if y is not None:
+            check(L.coda_bn_rows_sums(_ll(rows), _i(c), ptr(y), ptr(sums), ptr(_bn_scratch(c, dev)), stream_of(y)),
+                  "bn_rows_sums")
+        else:
+            check(L.coda_bn_partials_sums(_i(partials.shape[0]), _i(c), ptr(partials), ptr(sums), stream_of(partials)),
+                  "bn_partials_sums")
+        dist.all_reduce(sums, group=_BN_SYNC["group"])
+        check(L.coda_bn_stats_finalize_sums(_ll(rows * world), _i(c), ptr(sums), _f(bn.eps), _f(momentum),
+                                            ptr(bn.running_mean if track else None),
+                                            ptr(bn.running_var if track else None), ptr(gamma), ptr(beta), ptr(mean),
+                                            ptr(invstd), ptr(scale), ptr(shift), stream_of(src)), "bn_stats_finalize_sums")
+    return mean, invstd, scale, shift
+
+
+def bn_sync_backward_sums(s1: torch.Tensor, s2: torch.Tensor):
+    """(s1, s2) = local sums of dz and dz * xhat (they ARE dbeta / dgamma and stay local, as in torch's SyncBatchNorm);
+    the input gradient needs the global means: returns the rank-averaged copies (the kernels divide by the local row
+    count, so average = global sum / global count)."""
+    import torch.distributed as dist
+
+    t = torch.stack((s1, s2))
+    dist.all_reduce(t, op=dist.ReduceOp.AVG, group=_BN_SYNC["group"])
+    return t[0], t[1]
+
+
 class _BNActRows(torch.autograd.Function):
     """drop(relu(batch_norm(y))) on channels-last rows with batch statistics (training mode): statistics, one
     forward pass; backward = masked reduction + one pass (csrc/step_kernels.cu)."""
@@ -267,14 +329,19 @@ class _BNActRows(torch.autograd.Function):
             bn.num_batches_tracked.add_(1)
         if bn.momentum is None:
             raise NotImplementedError("cumulative-average BatchNorm momentum is not on the CoDA path")
-        mean = torch.empty(c, dtype=torch.float32, device=dev)
-        invstd = torch.empty(c, dtype=torch.float32, device=dev)
         out = torch.empty_like(yc)
         L = lib()
+        ctx.sync = bn_sync_world() > 1
         with torch.cuda.device(dev):
-            check(L.coda_bn_rows_stats(_ll(rows), _i(c), ptr(yc), _f(bn.eps), _f(bn.momentum),
-                                       ptr(bn.running_mean if track else None), ptr(bn.running_var if track else None),
-                                       ptr(mean), ptr(invstd), ptr(_bn_scratch(c, dev)), stream_of(yc)), "bn_rows_stats")
+            if ctx.sync:
+                mean, invstd, _, _ = bn_stats_synced(rows, c, bn, float(bn.momentum), track, gamma, beta, False, y=yc)
+            else:
+                mean = torch.empty(c, dtype=torch.float32, device=dev)
+                invstd = torch.empty(c, dtype=torch.float32, device=dev)
+                check(L.coda_bn_rows_stats(_ll(rows), _i(c), ptr(yc), _f(bn.eps), _f(bn.momentum),
+                                           ptr(bn.running_mean if track else None),
+                                           ptr(bn.running_var if track else None), ptr(mean), ptr(invstd),
+                                           ptr(_bn_scratch(c, dev)), stream_of(yc)), "bn_rows_stats")
             check(L.coda_bn_act_rows_fwd(_ll(rows), _i(c), ptr(yc), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta),
                                          _i(1 if relu else 0), _f(p), _uint(salt),
                                          ptr(_seed_dev(dev) if p > 0 else None), ptr(out), stream_of(yc)),
@@ -302,7 +369,8 @@ class _BNActRows(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(L.coda_bn_act_rows_bwd_reduce(*args, ptr(s1), ptr(s2), ptr(_bn_scratch(c, dev)), stream_of(y)),
                   "bn_act_rows_bwd_reduce")
-            check(L.coda_bn_act_rows_bwd(*args, ptr(s1), ptr(s2), ptr(dy), stream_of(y)), "bn_act_rows_bwd")
+            t1, t2 = bn_sync_backward_sums(s1, s2) if ctx.sync else (s1, s2)
+            check(L.coda_bn_act_rows_bwd(*args, ptr(t1), ptr(t2), ptr(dy), stream_of(y)), "bn_act_rows_bwd")
         if sg is not None:
             return dy, _sunk(sg), _sunk(sb), None, None, None, None
         return dy, s2, s1, None, None, None, None      # dgamma = sum dz * xhat, dbeta = sum dz
@@ -315,8 +383,9 @@ def bn_act_rows(h: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, relu
     the running buffers); eval mode normalises with the running statistics."""
     _need_cuda(h, "bn_act_rows")
     if isinstance(bn, torch.nn.SyncBatchNorm):
-        raise NotImplementedError("SyncBatchNorm modules are not executed by this package (per-GPU BatchNorm, "
-                                  "DESIGN.md section 7): do not call convert_sync_batchnorm on the model")
+        raise NotImplementedError("torch SyncBatchNorm modules are not executed by this package: keep the BatchNorm "
+                                  "modules and switch synchronisation on with ops.set_bn_sync(True) / "
+                                  "TrainStep(sync_bn=True) (DESIGN.md section 7)")
     c = h.shape[-1]
     if not (bn.affine and bn_channels_ok(c)):
         raise NotImplementedError(f"BatchNorm over {c} channels without affine parameters is not on the CoDA path")
@@ -453,7 +522,7 @@ def novel_candidates(boxes2d: torch.Tensor, valid: torch.Tensor, objectness: tor
 
 # --------------------------------------------------------------------------- attention
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, nhead: int, dropout_p: float = 0.0,
-              training: bool = False, causal: bool = False) -> torch.Tensor:
+              training: bool = False, causal: bool = False, mask=None) -> torch.Tensor:
     """Multi-head scaled-dot-product attention on projected, sequence-first tensors.
 
     q (Lq, B, E), k / v (Lk, B, E) -> (Lq, B, E).  The scale 1/sqrt(E/nhead) is applied to
@@ -462,7 +531,33 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, nhead: int, dro
     _need_cuda(q, "attention")
     from . import attention_sm100  # tcgen05 kernels (include/coda_attention.h)
 
-    return attention_sm100.attention(q, k, v, nhead, dropout_p, training, causal)
+    return attention_sm100.attention(q, k, v, nhead, dropout_p, training, causal, mask)
+
+
+def attention_mask_bits(mask: torch.Tensor, batch: int):
+    """boolean attention mask (True = not visible), (1 | B, Lq, Lk) -> packed (bits_q, bits_k) for ops.attention."""
+    _need_cuda(mask, "attention_mask_bits")
+    from . import attention_launch
+
+    return attention_launch.mask_bits(mask, batch)
+
+
+def radius_mask_bits(xyz: torch.Tensor, radius: float):
+    """packed mask of `cdist(xyz, xyz) >= radius` for points xyz (B, L, 3): the masked encoder's radius masks."""
+    _need_cuda(xyz, "radius_mask_bits")
+    from . import attention_launch
+
+    return attention_launch.radius_mask_bits(xyz, radius)
+
+
+def attention_fused(a: torch.Tensor, b, layout: str, nhead: int, dropout_p: float = 0.0, training: bool = False,
+                    mask=None) -> torch.Tensor:
+    """Self-attention straight from fused projections -- "qkv": a = (L, B, 3E); "qk_v": a = (L, B, 2E) q|k and
+    b = v (L, B, E).  Slices are read in place; the backward writes one packed gradient per fused projection."""
+    _need_cuda(a, "attention")
+    from . import attention_sm100
+
+    return attention_sm100.attention_fused(a, b, layout, nhead, dropout_p, training, mask)
 
 
 # --------------------------------------------------------------------------- CLIP crops
@@ -751,7 +846,7 @@ class _Linear(torch.autograd.Function):
         dx = dw = db = None
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[0]:
-            if a32_ok(dy):
+            if a32_ok(dy) and k % 4 == 0:
                 # dX (m, k) = dY (m, n) @ W (n, k): contraction over the ROWS of the forward weight planes
                 dx = gemm_a32(dy, _packed_weight(weight, False, ctx.nsplit), k, b_mn=True, nsplit=nsplit)
             else:

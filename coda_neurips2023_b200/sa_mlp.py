@@ -80,6 +80,8 @@ def _stats_affine(y: torch.Tensor, bn, gamma, beta):
     rows, c = y.shape
     momentum, track = _bn_bookkeeping(bn)
     dev = y.device
+    if ops.bn_sync_world() > 1:
+        return ops.bn_stats_synced(rows, c, bn, momentum, track, gamma, beta, True, y=y)
     cpad = ops._pad64(c)
     mean = torch.empty(c, dtype=torch.float32, device=dev)
     invstd = torch.empty(c, dtype=torch.float32, device=dev)
@@ -109,6 +111,8 @@ def _stats_from_partials(partials: torch.Tensor, rows: int, bn, gamma, beta, wan
     nblocks, _, c = partials.shape
     momentum, track = _bn_bookkeeping(bn)
     dev = partials.device
+    if ops.bn_sync_world() > 1:
+        return ops.bn_stats_synced(rows, c, bn, momentum, track, gamma, beta, want_affine, partials=partials)
     mean = torch.empty(c, dtype=torch.float32, device=dev)
     invstd = torch.empty(c, dtype=torch.float32, device=dev)
     scale = shift = None
@@ -167,6 +171,7 @@ class _SharedMLPMax(torch.autograd.Function):
                                                       ptr(gamma), ptr(beta), ptr(pooled), ptr(argmax), stream_of(x)),
                           "bn_relu_maxpool_rows")
         ctx.nl, ctx.group, ctx.small_k, ctx.nsplit = nl, group, small_k, nsplit
+        ctx.sync = ops.bn_sync_world() > 1
         ctx.save_for_backward(x, argmax, *ys, *means, *invstds, *scales, *shifts, *params)
         ctx.mark_non_differentiable(argmax)
         return pooled, argmax
@@ -215,6 +220,8 @@ class _SharedMLPMax(torch.autograd.Function):
                     grads[3 * li + 1], grads[3 * li + 2] = s2, s1        # dgamma, dbeta
                 else:
                     ops._sunk(sg), ops._sunk(sb)
+                if ctx.sync:      # the input gradient needs the means over every rank's rows; dgamma / dbeta stay local
+                    s1, s2 = ops.bn_sync_backward_sums(s1, s2)
                 sw = ops._sink(w)
                 if li == 0 and ctx.small_k:
                     if nl == 1:   # single block: expand the pooled gradient (not a CoDA configuration)

@@ -59,6 +59,25 @@ int coda_attention_fwd_packed_ex(int b, int h, int lq, int lk, int hd, int nspli
                                  const unsigned int *seed_dev, void *stream);
 
 /*
+ * Attention masks (reference: MaskedTransformerEncoder, models/transformer.py:146-211 -- the radius masks of
+ * `--enc_type masked`; nn.MultiheadAttention's boolean attn_mask in general).  Masks are bit-packed:
+ * bits[b][row][tile] is one 64-bit word per 64 columns, bit c set = column 64*tile + c is NOT visible from the row.
+ * bits_q is indexed by query row (forward, dQ kernel), bits_k by key row (dK/dV kernel: the transposed packing).
+ *   coda_attention_mask_pack: from a byte mask (nonzero = masked) addressed mask[b*stride_b + q*stride_q + k*stride_k]
+ *     (stride_b = 0 broadcasts one mask over the batch); bits_q has b*lq*ceil(lk/64) words, bits_k b*lk*ceil(lq/64).
+ *   coda_attention_mask_radius: masked iff |xyz_i - xyz_j| >= radius (torch.cdist(xyz, xyz) >= radius) for one set of
+ *     points xyz (b, l, 3) fp32; the mask is symmetric, `bits` (b*l*ceil(l/64) words) serves as bits_q and bits_k.
+ *   coda_attention_fwd_packed_masked: coda_attention_fwd_packed_ex with mask_q (NULL = no mask).  A query row with
+ *     no visible key yields NaN, as softmax over an all -inf row does in the reference.
+ */
+int coda_attention_mask_pack(int b, int lq, int lk, const unsigned char *mask, long long stride_b, long long stride_q,
+                             long long stride_k, unsigned long long *bits_q, unsigned long long *bits_k, void *stream);
+int coda_attention_mask_radius(int b, int l, const float *xyz, float radius, unsigned long long *bits, void *stream);
+int coda_attention_fwd_packed_masked(int b, int h, int lq, int lk, int hd, int nsplit, const void *workspace,
+                                     void *out, int out_half, float *lse, const unsigned long long *mask_q,
+                                     float dropout_p, unsigned int seed, const unsigned int *seed_dev, void *stream);
+
+/*
  * Backward of coda_attention_fwd (hd 64 or 128): two fused tcgen05 kernels (dQ row-wise; dK, dV
  * column-wise) that recompute the probabilities from `lse`, regenerate the dropout mask from the same
  * counter stream, and never write an (Lq x Lk) tensor.
@@ -71,6 +90,17 @@ int coda_attention_bwd(int b, int h, int lq, int lk, int hd, float scale, const 
                        const float *v, const float *out, const float *dout, const float *lse, float *dq,
                        float *dk, float *dv, float dropout_p, unsigned int seed,
                        const unsigned int *seed_dev, void *workspace, void *stream);
+
+/* As coda_attention_bwd with row strides and masks: q / k / v may be slices of one fused projection (ld_* = elements
+ * between consecutive (l, b) rows, multiples of 4), dq / dk / dv may be slices of one packed gradient buffer (the
+ * gradient of a fused q/k/v projection is then written in place, no concatenation), mask_q / mask_k as above (both
+ * NULL or both given). */
+int coda_attention_bwd_ex(int b, int h, int lq, int lk, int hd, float scale, const float *q, const float *k,
+                          const float *v, long long ld_q, long long ld_k, long long ld_v, const float *out,
+                          const float *dout, const float *lse, float *dq, float *dk, float *dv, long long ld_dq,
+                          long long ld_dk, long long ld_dv, const unsigned long long *mask_q,
+                          const unsigned long long *mask_k, float dropout_p, unsigned int seed,
+                          const unsigned int *seed_dev, void *workspace, void *stream);
 
 /* mult[bh][q][k] = keep(bh, q, k) ? 1/(1-p) : 0 -- the dropout factor the forward kernel applied,
  * regenerated from the counter hash (for a backward pass that materialises the probabilities). */

@@ -60,6 +60,22 @@ int coda_bn_stats_finalize(int nblocks, long long rows, int c, const float *part
                            float *running_mean, float *running_var, const float *gamma, const float *beta,
                            float *mean, float *invstd, float *scale, float *shift, void *stream);
 /*
+ * Synchronised BatchNorm (reference main.py:993, torch.nn.SyncBatchNorm.convert_sync_batchnorm): the statistics of a
+ * layer are taken over the batches of ALL ranks.  Per rank: sums[0..c) = column sums, sums[c..2c) = column sums of
+ * squares, in fp64, from a pass over y (coda_bn_rows_sums) or from the partials a GEMM epilogue wrote
+ * (coda_bn_partials_sums).  The caller all-reduces `sums` (ONE 16*c-byte collective per layer) and finishes with
+ * coda_bn_stats_finalize_sums(rows = global row count): mean, invstd, running buffers (unbiased variance over the
+ * global count) and optionally the folded affine map (scale / shift padded to a multiple of 64).
+ * Backward: the (s1, s2) sums of coda_*_bwd_reduce are all-reduced the same way (averaged: the kernels divide by
+ * the local row count); dgamma / dbeta stay the local sums, as in torch's SyncBatchNorm.
+ */
+int coda_bn_rows_sums(long long rows, int c, const float *y, double *sums, float *scratch, void *stream);
+int coda_bn_partials_sums(int nblocks, int c, const float *partial, double *sums, void *stream);
+int coda_bn_stats_finalize_sums(long long rows, int c, const double *sums, float eps, float momentum,
+                                float *running_mean, float *running_var, const float *gamma, const float *beta,
+                                float *mean, float *invstd, float *scale, float *shift, void *stream);
+
+/*
  * Per-channel coefficients of the BatchNorm(+ReLU) backward as a GEMM prologue (CODA_A32_BN_BWD*):
  *   dy = [y * scale + shift > 0] * scale * d + alpha * y + beta,
  *   alpha = -scale * invstd * s2 / rows,  beta = -scale * s1 / rows - alpha * mean   (padded to a multiple of 64)

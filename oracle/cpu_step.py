@@ -148,8 +148,31 @@ def installed(giou_fn=_giou_cpu, crop_fn=_crop_cpu):
         return F.dropout(out, drop_p, training)
 
     patch(ops, "bn_act_rows", _bn_act_rows)
-    patch(ops, "attention", lambda q, k, v, nhead, dropout_p=0.0, training=False, causal=False:
-          attention_sm100._math(q, k, v, nhead, dropout_p, training, causal))
+    # attention masks travel as (dense boolean (B, Lq, Lk), same) on the CPU path: the reference's own dense form
+    def _attention(q, k, v, nhead, dropout_p=0.0, training=False, causal=False, mask=None):
+        return attention_sm100._math(q, k, v, nhead, dropout_p, training, causal,
+                                     attn_mask=None if mask is None else mask[0])
+
+    def _attention_fused(a, b, layout, nhead, dropout_p=0.0, training=False, mask=None):
+        e = a.shape[-1] // (3 if layout == "qkv" else 2)
+        q, k = a[..., :e], a[..., e: 2 * e]
+        v = a[..., 2 * e:] if layout == "qkv" else b
+        return _attention(q, k, v, nhead, dropout_p, training, False, mask)
+
+    def _mask_bits(mask, batch):
+        m = mask.to(torch.bool)
+        m = m.unsqueeze(0) if m.dim() == 2 else m
+        m = m.expand(batch, -1, -1)
+        return m, m
+
+    def _radius_mask(xyz, radius):       # reference models/transformer.py:155-162
+        m = torch.cdist(xyz, xyz, p=2) >= radius
+        return m, m
+
+    patch(ops, "attention", _attention)
+    patch(ops, "attention_fused", _attention_fused)
+    patch(ops, "attention_mask_bits", _mask_bits)
+    patch(ops, "radius_mask_bits", _radius_mask)
     if giou_fn is not None:
         patch(ops, "giou3d", giou_fn)
     if crop_fn is not None:

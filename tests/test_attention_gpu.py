@@ -115,3 +115,71 @@ def test_attention_forward_reads_fp16_slices_of_a_fused_projection_in_place():
     o_s, _ = attention_launch.forward(q2, k2, v2, 4)
     o_c, _ = attention_launch.forward(q2.contiguous(), k2.contiguous(), v2.contiguous(), 4)
     assert torch.equal(o_s, o_c)
+
+
+@pytest.mark.parametrize("lq,lk,b,h,hd", [(256, 256, 2, 4, 64), (2048, 2048, 1, 4, 64), (130, 200, 2, 2, 64),
+                                          (256, 2048, 2, 4, 128), (100, 77, 1, 2, 128)])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_masked_attention_forward_backward_vs_fp64(lq, lk, b, h, hd, p):
+    """Boolean attn_mask (True = not visible; nn.MultiheadAttention's convention, the reference's masked encoder
+    transformer.py:146-211) applied inside the fused kernels, forward and backward, against the fp64 formula.  The
+    masks include rows whose first key tiles are entirely masked (running max stays -inf for a while)."""
+    torch.manual_seed(lq * 3 + lk)
+    e = h * hd
+    q = torch.randn(lq, b, e, device="cuda") * 1.2
+    k = torch.randn(lk, b, e, device="cuda") * 1.2
+    v = torch.randn(lk, b, e, device="cuda")
+    mask = torch.rand(b, lq, lk, device="cuda") < 0.6
+    mask[:, : lq // 2, : min(lk, 192) // 2] = True             # leading key tiles fully masked for half the rows
+    mask[:, :, lk - 1] = False                                 # every row keeps at least one key
+    bits = attention_launch.mask_bits(mask, b)
+    attention_launch.seed_counter(q.device).fill_(77)
+    out, lse = attention_launch.forward(q, k, v, h, dropout_p=p, salt=5, mask=bits)
+    g = torch.randn_like(out)
+    dq, dk, dv = attention_launch.backward(q, k, v, out, g, lse, h, p, 5, mask=bits)
+    keep = attention_launch.dropout_keep(b * h, lq, lk, p, 5, q.device) if p > 0 else None
+    q64, k64, v64 = (t.double().requires_grad_(True) for t in (q, k, v))
+    ref = attention_sm100._math(q64, k64, v64, h, p, False, False, keep, attn_mask=mask)
+    assert torch.isfinite(out).all()
+    assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 5e-6
+    rq, rk, rv = torch.autograd.grad(ref, (q64, k64, v64), g.double())
+    for name, got, exp in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+        err = ((got.double() - exp).abs().max() / exp.abs().max()).item()
+        assert err < 2e-4, f"{name}: rel err {err:.2e}"
+
+
+def test_radius_mask_bits_equal_cdist_mask():
+    """The packed radius mask built from coordinates == packing the reference's `cdist(xyz, xyz) >= radius`
+    (points exactly on the threshold aside: none in this draw), and broadcast / per-scene packing agree."""
+    torch.manual_seed(4)
+    xyz = torch.rand(3, 1000, 3, device="cuda") * 3
+    radius = 0.4 ** 2 * 4
+    dense = torch.cdist(xyz.double(), xyz.double()) >= radius
+    bq, bk = attention_launch.radius_mask_bits(xyz, radius)
+    eq, ek = attention_launch.mask_bits(dense, 3)
+    assert bq is bk and torch.equal(bq, eq) and torch.equal(bk, ek)
+    one = attention_launch.mask_bits(dense[0], 3)          # (Lq, Lk) mask broadcast over the batch
+    assert torch.equal(one[0][1], eq[0]) and torch.equal(one[1][2], ek[0])
+
+
+def test_fused_projection_layouts_match_separate_tensors():
+    """attention_fused ("qkv" / "qk_v": slices of ONE projection read in place, ONE packed gradient written by the
+    backward) == the three-tensor call on copies, values and gradients bit for bit."""
+    torch.manual_seed(6)
+    l, b, h, e = 300, 2, 4, 256
+    for layout in ("qkv", "qk_v"):
+        width = 3 * e if layout == "qkv" else 2 * e
+        a = torch.randn(l, b, width, device="cuda", requires_grad=True)
+        vsep = torch.randn(l, b, e, device="cuda", requires_grad=True) if layout == "qk_v" else None
+        out = attention_sm100.attention_fused(a, vsep, layout, h)
+        g = torch.randn_like(out)
+        grads = torch.autograd.grad(out, (a,) if vsep is None else (a, vsep), g)
+        parts = [a.detach()[..., i * e: (i + 1) * e].clone().requires_grad_(True) for i in range(width // e)]
+        if vsep is not None:
+            parts.append(vsep.detach().clone().requires_grad_(True))
+        ref = attention_sm100.attention(parts[0], parts[1], parts[2], h)
+        rg = torch.autograd.grad(ref, parts, g)
+        assert torch.equal(out, ref)
+        assert grads[0].is_contiguous() and torch.equal(grads[0], torch.cat(rg[: width // e], dim=-1))
+        if vsep is not None:
+            assert torch.equal(grads[1], rg[2])

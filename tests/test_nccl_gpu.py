@@ -54,7 +54,7 @@ def _args():
                                loss_predicted_region_embed_l1_weight=0.0)
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, sync_bn=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
 
@@ -68,14 +68,15 @@ def _worker(rank, world, port, ret):
     model, crit = _build(100 + rank, args)            # different initialisation per rank
     model = model.to(dev).train()
     model.clip_model.eval()
-    _bn_eval(model)
+    if not sync_bn:
+        _bn_eval(model)
     crit = crit.to(dev)
     full = synthetic.make_batch(4, 3000, seed=7)
     mine = {k: v[rank * 2: rank * 2 + 2] for k, v in full.items()}
     batch = synthetic.to_device(mine, dev)
     sel = np.random.RandomState(5).choice(128, size=(4, 32))      # the same crop boxes as the single-GPU run
     model.draw_box_selection = lambda bsz: sel[rank * 2: rank * 2 + 2].astype(np.int64)
-    step = TrainStep(args, model, crit, dev, nbuckets=3)
+    step = TrainStep(args, model, crit, dev, nbuckets=3, sync_bn=sync_bn)
     step.prepare(batch)
     w0 = step.flat.flat_param.detach().clone()
     # one eager backward through the step body WITHOUT the optimiser: capture the reduced gradient
@@ -87,6 +88,9 @@ def _worker(rank, world, port, ret):
     launched_early = sum(step.reducer.launched)
     step.reducer.finish()
     grads = {n: p.grad.detach().clone().cpu() for n, p in model.named_parameters() if p.requires_grad}
+    if rank == 0:
+        ret["loss"] = float(loss)
+        ret["bn_mean"] = {n: b.detach().clone().cpu() for n, b in model.named_buffers() if n.endswith("running_mean")}
     # drop the eager graph: its AccumulateGrad nodes were created on the default stream and would be reused (with
     # that stream) by the capture below
     del out, loss
@@ -147,3 +151,45 @@ def test_two_rank_step_equals_concatenated_batch(built_lib):
             worst = max(worst, float((g - e).abs().max()) / scale)
     print(f"PARITY nccl_2rank: max relative deviation of the all-reduced gradient from the 1-GPU gradient {worst:.2e}")
     assert worst < 2e-2     # 2 bf16 planes in the backward, different reduction orders
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_rank_sync_batchnorm_equals_concatenated_batch(built_lib):
+    """TrainStep(sync_bn=True): BatchNorm in TRAINING mode with statistics all-reduced over the ranks (the
+    reference's convert_sync_batchnorm, main.py:993).  Two ranks x 2 scenes must then give the gradient -- and the
+    running statistics -- of one GPU on the 4-scene batch: the SyncBN exchange (fp64 column sums forward, averaged
+    (sum dz, sum dz xhat) backward, 18 layers) is what makes data parallelism batch-equivalent."""
+    import torch.multiprocessing as mp
+
+    from coda_neurips2023_b200 import synthetic
+
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret, True), nprocs=2, join=True)
+    assert ret["spread_after_steps"] == 0.0, "ranks diverged"
+    args = _args()
+    args.ngpus = 1
+    model, crit = _build(100, args)
+    model = model.cuda().train()
+    model.clip_model.eval()
+    crit = crit.cuda()
+    sel = np.random.RandomState(5).choice(128, size=(4, 32))
+    model.draw_box_selection = lambda bsz: sel.astype(np.int64)
+    batch = synthetic.to_device(synthetic.make_batch(4, 3000, seed=7), "cuda")
+    out = model(batch, curr_epoch=0)
+    loss, _ = crit(out, batch)
+    loss.backward()
+    worst = 0.0
+    for n, p in model.named_parameters():
+        if p.requires_grad and p.grad is not None:
+            g, e = ret["grads"][n].double(), p.grad.detach().cpu().double()
+            scale = max(float(e.abs().max()), 1e-5)
+            worst = max(worst, float((g - e).abs().max()) / scale)
+    stat = 0.0
+    for n, b in model.named_buffers():
+        if n.endswith("running_mean"):
+            e = b.detach().cpu().double()
+            stat = max(stat, float((ret["bn_mean"][n].double() - e).abs().max()) / max(float(e.abs().max()), 1e-6))
+    print(f"PARITY nccl_2rank_syncbn: gradient deviation {worst:.2e}, running-mean deviation {stat:.2e}")
+    assert stat < 1e-4
+    assert worst < 2e-2
