@@ -31,7 +31,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .utils.dist import get_world_size, is_distributed
+from .utils.dist import get_world_size, is_distributed, is_primary
 
 
 def adjust_learning_rate(args, optimizer, curr_epoch: float) -> float:
@@ -492,3 +492,30 @@ class TrainStep:
         self.optimizer.step()                          # global-norm clip + AdamW, two kernels
         ops.invalidate_weight_cache()  # packed bf16 weight planes are stale now
         return loss.detach(), loss_dict
+
+
+@torch.no_grad()
+def evaluate(args, curr_epoch, model, criterion, dataset_config, dataset_loader, logger=None, curr_train_iter=0,
+             if_real_test=False, if_cmp_class=False):
+    """Evaluation loop (reference engine.py:2553-2661): model in eval mode -> (optional loss) -> APCalculator.
+    Differences are implementation-only: the AP bookkeeping of a batch runs on the device (utils/ap_calculator.py,
+    five kernel launches, no host copies), and under data parallelism the ranks do not all-gather their point
+    clouds and outputs (`all_gather_dict`, :2634-2636) -- each rank matches its own scenes and only the (score,
+    true-positive) records would have to be gathered; call `compute_metrics()` on the returned calculator."""
+    from .utils.ap_calculator import APCalculator
+
+    ap_calculator = APCalculator(dataset_config=dataset_config, ap_iou_thresh=[0.25, 0.5],
+                                 class2type_map=getattr(dataset_config, "class2type", None), exact_eval=True, args=args)
+    device = next(model.parameters()).device
+    model.eval()
+    loss_sum, nloss = 0.0, 0
+    for batch in dataset_loader:
+        batch = {k: (v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+        outputs = model(batch, if_real_test=if_real_test, if_cmp_class=if_cmp_class)
+        if criterion is not None:
+            loss, _ = criterion(outputs, batch)
+            loss_sum, nloss = loss_sum + loss.detach(), nloss + 1
+        ap_calculator.step_meter(outputs, batch)
+    if logger is not None and nloss and is_primary():
+        logger.log_scalars({"loss": float(loss_sum) / nloss}, curr_train_iter, prefix="Test/")
+    return ap_calculator

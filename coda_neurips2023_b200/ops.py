@@ -167,9 +167,10 @@ def layer_norm_half(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, e
     xc = x.contiguous()
     c = xc.shape[-1]
     y = torch.empty_like(xc)
+    w32, b32 = _f32c(weight), _f32c(bias)      # held until the launch (see boxes_in_image)
     with torch.cuda.device(x.device):
-        st = lib().coda_layer_norm_fwd_half(_ll(xc.numel() // c), _i(c), _f(eps), ptr(xc), ptr(_f32c(weight)),
-                                            ptr(_f32c(bias)), ptr(y), stream_of(x))
+        st = lib().coda_layer_norm_fwd_half(_ll(xc.numel() // c), _i(c), _f(eps), ptr(xc), ptr(w32), ptr(b32), ptr(y),
+                                            stream_of(x))
     check(st, "layer_norm_fwd_half")
     return y
 
@@ -487,12 +488,14 @@ def boxes_in_image(corners_xyz: torch.Tensor, size_unnorm: torch.Tensor, inputs:
     zx = f64(inputs["zx_flip_array"], (b,)) if "zx_flip_array" in inputs else None
     boxes = torch.empty((b, q, 4), dtype=torch.int32, device=dev)
     valid = torch.empty((b, q), dtype=torch.uint8, device=dev)
+    # every converted operand is held in a local until the launch has been issued (a temporary that dies inside the
+    # argument list would hand its block to the next conversion)
+    cx, su = _f32c(corners_xyz), _f32c(size_unnorm)
+    ow, oh, xo, yo = (i64(inputs[k]) for k in ("ori_width", "ori_height", "x_offset", "y_offset"))
     with torch.cuda.device(dev):
-        st = lib().coda_boxes_in_image(_i(b), _i(q), ptr(_f32c(corners_xyz)), ptr(_f32c(size_unnorm)), ptr(scale), ptr(rot),
-                                       ptr(flip), ptr(zx), ptr(K), ptr(Rtilt), ptr(i64(inputs["ori_width"])),
-                                       ptr(i64(inputs["ori_height"])), ptr(i64(inputs["x_offset"])),
-                                       ptr(i64(inputs["y_offset"])), ptr(img_flip), ptr(flip_len), ptr(boxes), ptr(valid),
-                                       stream_of(corners_xyz))
+        st = lib().coda_boxes_in_image(_i(b), _i(q), ptr(cx), ptr(su), ptr(scale), ptr(rot), ptr(flip), ptr(zx), ptr(K),
+                                       ptr(Rtilt), ptr(ow), ptr(oh), ptr(xo), ptr(yo), ptr(img_flip), ptr(flip_len),
+                                       ptr(boxes), ptr(valid), stream_of(corners_xyz))
     check(st, "boxes_in_image")
     return boxes, valid.bool()
 
@@ -511,10 +514,10 @@ def novel_candidates(boxes2d: torch.Tensor, valid: torch.Tensor, objectness: tor
     vd = valid.to(torch.uint8).contiguous()
     cand = torch.empty((b, cap), dtype=torch.int32, device=bx.device)
     count = torch.empty((b, 2), dtype=torch.int32, device=bx.device)
+    ob, pc, gc, gp = _f32c(objectness), _f32c(pred_corners), _f32c(gt_corners), _f32c(gt_present)
     with torch.cuda.device(bx.device):
-        st = lib().coda_novel_candidates(_i(b), _i(q), _i(g), _i(cap), ptr(bx), ptr(vd), ptr(_f32c(objectness)),
-                                         ptr(_f32c(pred_corners)), ptr(_f32c(gt_corners)), ptr(_f32c(gt_present)),
-                                         _f(nms_iou), _f(gt_iou), _f(min_objectness), ptr(cand), ptr(count),
+        st = lib().coda_novel_candidates(_i(b), _i(q), _i(g), _i(cap), ptr(bx), ptr(vd), ptr(ob), ptr(pc), ptr(gc),
+                                         ptr(gp), _f(nms_iou), _f(gt_iou), _f(min_objectness), ptr(cand), ptr(count),
                                          stream_of(bx))
     check(st, "novel_candidates")
     return cand, count

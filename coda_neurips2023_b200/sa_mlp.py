@@ -216,12 +216,16 @@ class _SharedMLPMax(torch.autograd.Function):
                     check(L.coda_bn_relu_bwd_reduce(_ll(rows), _i(cout), ptr(y), ptr(dz), ptr(mean), ptr(invstd),
                                                     ptr(gamma), ptr(beta), ptr(s1), ptr(s2), ptr(scratch), stream_of(x)),
                           "bn_relu_bwd_reduce")
+                loc1, loc2 = s1, s2
+                if ctx.sync:
+                    # the input gradient needs the means over every rank's rows; dgamma / dbeta stay the local sums.
+                    # Taken BEFORE the sink is notified: the notification may start the all-reduce of that range of
+                    # the flat gradient on the side stream, which rewrites s1 / s2 in place
+                    s1, s2 = ops.bn_sync_backward_sums(s1, s2)
                 if sg is None:
-                    grads[3 * li + 1], grads[3 * li + 2] = s2, s1        # dgamma, dbeta
+                    grads[3 * li + 1], grads[3 * li + 2] = loc2, loc1    # dgamma, dbeta
                 else:
                     ops._sunk(sg), ops._sunk(sb)
-                if ctx.sync:      # the input gradient needs the means over every rank's rows; dgamma / dbeta stay local
-                    s1, s2 = ops.bn_sync_backward_sums(s1, s2)
                 sw = ops._sink(w)
                 if li == 0 and ctx.small_k:
                     if nl == 1:   # single block: expand the pooled gradient (not a CoDA configuration)

@@ -179,12 +179,15 @@ def test_two_rank_sync_batchnorm_equals_concatenated_batch(built_lib):
     out = model(batch, curr_epoch=0)
     loss, _ = crit(out, batch)
     loss.backward()
-    worst = 0.0
+    devs = []
     for n, p in model.named_parameters():
         if p.requires_grad and p.grad is not None:
             g, e = ret["grads"][n].double(), p.grad.detach().cpu().double()
             scale = max(float(e.abs().max()), 1e-5)
-            worst = max(worst, float((g - e).abs().max()) / scale)
+            devs.append((float((g - e).abs().max()) / scale, n))
+    devs.sort(reverse=True)
+    worst = devs[0][0]
+    print("largest gradient deviations:", [(f"{d:.1e}", n) for d, n in devs[:5]])
     stat = 0.0
     for n, b in model.named_buffers():
         if n.endswith("running_mean"):
