@@ -139,9 +139,19 @@ class VisionTransformer(nn.Module):
         all_tokens = self.ln_post(x)
         x = all_tokens[:, 0, :]
         if self.proj is not None:
-            x = x @ self.proj
-            all_tokens = all_tokens @ self.proj
+            x, all_tokens = self._project(x), self._project(all_tokens)
         return x, all_tokens
+
+    def _project(self, x):
+        """x @ proj (reference CLIP/clip/model.py:655-657).  fp16 on the device: the tcgen05 GEMM with the transposed
+        projection as its K-major weight (cached; the tower is frozen)."""
+        if not (x.is_cuda and x.dtype == torch.float16 and x.shape[-1] % 64 == 0):
+            return x @ self.proj
+        key = (self.proj.data_ptr(), self.proj._version)
+        if getattr(self, "_proj_t_key", None) != key:
+            self._proj_t = self.proj.detach().t().contiguous()
+            self._proj_t_key = key
+        return _linear(x, self._proj_t, None)
 
 
 class CLIP(nn.Module):

@@ -153,46 +153,62 @@ def test_two_rank_step_equals_concatenated_batch(built_lib):
     assert worst < 2e-2     # 2 bf16 planes in the backward, different reduction orders
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_two_rank_sync_batchnorm_equals_concatenated_batch(built_lib):
-    """TrainStep(sync_bn=True): BatchNorm in TRAINING mode with statistics all-reduced over the ranks (the
-    reference's convert_sync_batchnorm, main.py:993).  Two ranks x 2 scenes must then give the gradient -- and the
-    running statistics -- of one GPU on the 4-scene batch: the SyncBN exchange (fp64 column sums forward, averaged
-    (sum dz, sum dz xhat) backward, 18 layers) is what makes data parallelism batch-equivalent."""
-    import torch.multiprocessing as mp
-
+def _single_gpu_train_bn_grads(perm):
+    """gradient and BatchNorm running means of ONE GPU on the 4-scene batch (BatchNorm in training mode), scenes
+    visited in the order `perm`: mathematically the same batch, a different order of every reduction"""
     from coda_neurips2023_b200 import synthetic
 
-    mgr = mp.Manager()
-    ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), ret, True), nprocs=2, join=True)
-    assert ret["spread_after_steps"] == 0.0, "ranks diverged"
     args = _args()
     args.ngpus = 1
     model, crit = _build(100, args)
     model = model.cuda().train()
     model.clip_model.eval()
     crit = crit.cuda()
-    sel = np.random.RandomState(5).choice(128, size=(4, 32))
+    sel = np.random.RandomState(5).choice(128, size=(4, 32))[perm]
     model.draw_box_selection = lambda bsz: sel.astype(np.int64)
-    batch = synthetic.to_device(synthetic.make_batch(4, 3000, seed=7), "cuda")
+    full = synthetic.make_batch(4, 3000, seed=7)
+    batch = synthetic.to_device({k: v[perm] for k, v in full.items()}, "cuda")
     out = model(batch, curr_epoch=0)
     loss, _ = crit(out, batch)
     loss.backward()
-    devs = []
-    for n, p in model.named_parameters():
-        if p.requires_grad and p.grad is not None:
-            g, e = ret["grads"][n].double(), p.grad.detach().cpu().double()
-            scale = max(float(e.abs().max()), 1e-5)
-            devs.append((float((g - e).abs().max()) / scale, n))
+    grads = {n: p.grad.detach().cpu().double() for n, p in model.named_parameters() if p.requires_grad and p.grad is not None}
+    means = {n: b.detach().cpu().double() for n, b in model.named_buffers() if n.endswith("running_mean")}
+    return grads, means
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_rank_sync_batchnorm_equals_concatenated_batch(built_lib):
+    """TrainStep(sync_bn=True): BatchNorm in TRAINING mode with statistics all-reduced over the ranks (the
+    reference's convert_sync_batchnorm, main.py:993).  Two ranks x 2 scenes must then give the gradient -- and the
+    running statistics -- of one GPU on the 4-scene batch: the SyncBN exchange (fp64 column sums forward, averaged
+    (sum dz, sum dz xhat) backward, 18 layers) is what makes data parallelism batch-equivalent.
+
+    Training-mode BatchNorm subtracts batch means in its backward, which amplifies the rounding of the two-plane
+    gradient GEMMs by the cancellation factor (a LayerNorm bias in front of a Linear + BatchNorm has a gradient that is
+    zero in exact arithmetic: what is measured there is pure rounding).  The yardstick is therefore measured, not
+    assumed: the same single-GPU batch with its scenes in another order -- identical mathematics, another order of
+    every reduction -- and each parameter is held to a few times ITS OWN noise."""
+    import torch.multiprocessing as mp
+
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret, True), nprocs=2, join=True)
+    assert ret["spread_after_steps"] == 0.0, "ranks diverged"
+    ref, ref_means = _single_gpu_train_bn_grads(np.array([0, 1, 2, 3]))
+    alt, _ = _single_gpu_train_bn_grads(np.array([2, 3, 0, 1]))
+    devs, worst_excess = [], 0.0
+    for n, e in ref.items():
+        scale = max(float(e.abs().max()), 1e-5)
+        dev = float((ret["grads"][n].double() - e).abs().max()) / scale
+        noise = float((alt[n] - e).abs().max()) / scale
+        devs.append((dev, noise, n))
+        worst_excess = max(worst_excess, dev / max(4.0 * noise, 2e-3))
     devs.sort(reverse=True)
-    worst = devs[0][0]
-    print("largest gradient deviations:", [(f"{d:.1e}", n) for d, n in devs[:5]])
-    stat = 0.0
-    for n, b in model.named_buffers():
-        if n.endswith("running_mean"):
-            e = b.detach().cpu().double()
-            stat = max(stat, float((ret["bn_mean"][n].double() - e).abs().max()) / max(float(e.abs().max()), 1e-6))
-    print(f"PARITY nccl_2rank_syncbn: gradient deviation {worst:.2e}, running-mean deviation {stat:.2e}")
+    stat = max(float((ret["bn_mean"][n].double() - e).abs().max()) / max(float(e.abs().max()), 1e-6)
+               for n, e in ref_means.items())
+    print("largest gradient deviations (2 ranks vs 1 GPU | same GPU, scenes reordered):",
+          [(f"{d:.1e}", f"{z:.1e}", n) for d, z, n in devs[:6]])
+    print(f"PARITY nccl_2rank_syncbn: worst deviation / (4 x reorder noise, floor 2e-3) = {worst_excess:.2f}, "
+          f"running-mean deviation {stat:.2e}")
     assert stat < 1e-4
-    assert worst < 2e-2
+    assert worst_excess < 1.0
