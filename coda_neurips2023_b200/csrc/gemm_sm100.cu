@@ -587,7 +587,10 @@ int coda_gemm_nt_res(int nsplit, int is_fp16, int batch, int m, int n, int kpad,
   if (is_fp16 && nsplit != 1) return CODA_EINVAL;
   if (batch == 0 || m == 0 || n == 0) return CODA_OK;
   if (!a || !b || !c || kpad == 0 || batch > 65535) return CODA_EINVAL;
-  const int bn = n <= 64 ? 64 : 128;
+  // fp16 tower GEMMs with wide outputs: a 128 x 256 tile moves 48 KB per k-block for twice the flops of a 128 x 128
+  // tile (32 KB) -- these shapes are L2 -> SM bandwidth bound, not tensor bound.  Narrow outputs (N = 768: 300 tiles
+  // on 148 SMs) keep the 128-wide tile for its finer wave quantisation.
+  const int bn = n <= 64 ? 64 : ((is_fp16 && n % 256 == 0 && n >= 1536) ? 256 : 128);
   GemmMaps maps;
   const char *ap = (const char *)a, *bp = (const char *)b;
   for (int p = 0; p < nsplit; ++p) {
@@ -605,6 +608,7 @@ int coda_gemm_nt_res(int nsplit, int is_fp16, int batch, int m, int n, int kpad,
                                        residual, ldr)
   if (is_fp16) {
     if (bn == 64) CODA_GEMM(1, 64, 6, true);
+    if (bn == 256) CODA_GEMM(1, 256, 4, true);
     CODA_GEMM(1, 128, 6, true);
   }
   if (nsplit == 1) {

@@ -299,6 +299,8 @@ class TrainStep:
         self.static_out = None
         self._sel_host = None
         self._nsel = getattr(model, "distillation_box_num", 32)
+        self._pack_requests = None          # (weight, transposed, nsplit) planes a step asks for; recorded on step one
+        self._pack_stream = None
 
     # ------------------------------------------------------------------ host-side per-step work
     def to_device(self, batch_host: dict) -> dict:
@@ -485,9 +487,24 @@ class TrainStep:
         attention_launch.advance_seed(self.device)
         self.flat.zero_grad()
         self.reducer.start()
+        # operand planes of every weight the step will ask for, packed on a side stream while the main stream runs the
+        # furthest-point sampling; the request list is recorded on the first step
+        recording = self._pack_requests is None
+        if recording:
+            ops.record_weight_packs(True)
+        else:
+            if self._pack_stream is None:
+                self._pack_stream = torch.cuda.Stream(device=self.device)
+            self._pack_stream.wait_stream(torch.cuda.current_stream(self.device))
+            ops.prepack_weights(self._pack_requests, self._pack_stream)
         outputs = self.model(batch, curr_epoch=int(curr_epoch))
         loss, loss_dict = self.criterion(outputs, batch)
         loss.backward()                                # range all-reduces start from the gradient hooks
+        if recording:
+            self._pack_requests = ops.record_weight_packs(False)
+        elif ops._PACK_JOIN is not None:               # no consumer joined (cannot happen with packed weights in use)
+            torch.cuda.current_stream(self.device).wait_stream(self._pack_stream)
+            ops._PACK_JOIN = None
         self.reducer.finish()
         self.optimizer.step()                          # global-norm clip + AdamW, two kernels
         ops.invalidate_weight_cache()  # packed bf16 weight planes are stale now

@@ -753,6 +753,32 @@ USE_TN_WGRAD = True  # weight gradients from the row-packed operands (MN-major M
 # --------------------------------------------------------------------------- Linear on the tcgen05 GEMM
 _WEIGHT_EPOCH = 0
 _WEIGHT_CACHE: dict = {}
+# Weight planes depend on nothing but the parameters: a step can pack ALL of them up front on a side stream, under
+# the furthest-point sampling that opens the forward (64 CTAs, 1.1 ms, nothing else to run beside it) instead of one
+# ~4 us launch in front of every GEMM.  _PACK_LOG records the (weight, transposed, nsplit) requests of a step;
+# _PACK_JOIN is the side stream the first consumer of a step has to wait for.
+_PACK_LOG: list | None = None
+_PACK_JOIN = None
+
+
+def record_weight_packs(on: bool):
+    """start recording / stop and return the list of weight-plane requests"""
+    global _PACK_LOG
+    if on:
+        _PACK_LOG = []
+        return None
+    log, _PACK_LOG = _PACK_LOG, None
+    return log
+
+
+def prepack_weights(requests, side_stream) -> None:
+    """pack every requested weight on `side_stream` (which has been ordered after the parameter update); the first
+    _packed_weight call of the step joins it."""
+    global _PACK_JOIN
+    with torch.cuda.stream(side_stream):
+        for w, transposed, nsplit in requests:
+            _packed_weight(w, transposed, nsplit)
+    _PACK_JOIN = side_stream
 
 
 _ACT_CACHE: dict = {}   # packed planes of activations that several layers consume within one step
@@ -784,9 +810,16 @@ def _packed_rows(x: torch.Tensor, nsplit: int) -> torch.Tensor:
 
 def _packed_weight(w: torch.Tensor, transposed: bool, nsplit: int) -> torch.Tensor:
     """Planes of W (N, K) as a B operand: rows = N, k = K; or of W^T (rows = K, k = N) when transposed."""
+    global _PACK_JOIN
+    if _PACK_JOIN is not None and torch.cuda.current_stream(w.device) != _PACK_JOIN:
+        torch.cuda.current_stream(w.device).wait_stream(_PACK_JOIN)      # once per step: planes packed up front
+        _PACK_JOIN = None
     key = (w.data_ptr(), tuple(w.shape), w._version, _WEIGHT_EPOCH, transposed, nsplit)
     hit = _WEIGHT_CACHE.get(key)
     if hit is None:
+        if _PACK_LOG is not None:
+            # detached: a recorded slice of a parameter must not keep the recording step's autograd graph alive
+            _PACK_LOG.append((w.detach(), transposed, nsplit))
         n, k = w.shape
         wd = w.detach()
         planes = pack_split(wd, k, n, 1, k, nsplit) if transposed else pack_split(wd, n, k, k, 1, nsplit)
