@@ -133,6 +133,9 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
   constexpr int B_TILE = BN * BK * 2;
   constexpr int STAGE = NSPLIT * (A_TILE + B_TILE);
   constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
+  // tensor-memory allocations are powers of two: two accumulators of 192 columns take the 512-column allocation
+  constexpr uint32_t TMEM_ALLOC = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
+                                  : 2 * ACC_COLS <= 256 ? 256 : 512;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -174,7 +177,7 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     mbar_fence_init_cluster();
   }
-  if (warp == 2) tmem_alloc(&tmem_slot, 2 * ACC_COLS);
+  if (warp == 2) tmem_alloc(&tmem_slot, TMEM_ALLOC);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -461,7 +464,7 @@ gemm_nt_kernel(const __grid_constant__ GemmMaps maps, int m, int n, int kpad, in
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 2 * ACC_COLS);
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_ALLOC);
 }
 
 template <int NSPLIT, int BN, int STAGES, bool FP16, bool MN = false>
@@ -590,7 +593,12 @@ int coda_gemm_nt_res(int nsplit, int is_fp16, int batch, int m, int n, int kpad,
   // fp16 tower GEMMs with wide outputs: a 128 x 256 tile moves 48 KB per k-block for twice the flops of a 128 x 128
   // tile (32 KB) -- these shapes are L2 -> SM bandwidth bound, not tensor bound.  Narrow outputs (N = 768: 300 tiles
   // on 148 SMs) keep the 128-wide tile for its finer wave quantisation.
-  const int bn = n <= 64 ? 64 : ((is_fp16 && n % 256 == 0 && n >= 1536) ? 256 : 128);
+  // N = 768 (attention / MLP output projections of the ViT): 192-wide tiles give 400 work items (2.7 waves) at
+  // 77 flop/B instead of 600 (4.05 waves -> 5 rounds) at 64 flop/B.
+  const int bn = n <= 64 ? 64
+                 : (is_fp16 && n % 256 == 0 && n >= 1536) ? 256
+                 : (is_fp16 && n % 192 == 0 && n >= 384)  ? 192
+                                                          : 128;
   GemmMaps maps;
   const char *ap = (const char *)a, *bp = (const char *)b;
   for (int p = 0; p < nsplit; ++p) {
@@ -609,6 +617,7 @@ int coda_gemm_nt_res(int nsplit, int is_fp16, int batch, int m, int n, int kpad,
   if (is_fp16) {
     if (bn == 64) CODA_GEMM(1, 64, 6, true);
     if (bn == 256) CODA_GEMM(1, 256, 4, true);
+    if (bn == 192) CODA_GEMM(1, 192, 5, true);
     CODA_GEMM(1, 128, 6, true);
   }
   if (nsplit == 1) {

@@ -67,6 +67,13 @@ class MultiheadAttention(nn.Module):
             out = ops.attention(q, k, v, self.num_heads, self.dropout, self.training, mask=mask)
         return self.out_proj(out), None
 
+    def forward_bank(self, query: Tensor, bank, token, idx: int):
+        """cross-attention whose keys / values were projected for all layers at once (ops.KVBank)"""
+        e = self.embed_dim
+        q = ops.linear(query, self.in_proj_weight[:e], self.in_proj_bias[:e])
+        out = ops.attention_bank(q, bank, token, idx, self.num_heads, self.dropout, self.training)
+        return self.out_proj(out), None
+
     def _packed_mask(self, attn_mask, key_padding_mask, batch, lq, lk):
         if attn_mask is None and key_padding_mask is None:
             return None
@@ -264,13 +271,18 @@ class TransformerDecoder(nn.Module):
             raise NotImplementedError("attention weights are not materialised by the fused kernel")
         # key of every cross-attention is memory + pos: formed once, not once per layer
         mem_key = memory if pos is None else memory + pos
+        # ... and so are the K / V projections of all layers: two GEMMs instead of 2 x num_layers (ops.KVBank)
+        kv = None
+        cross = [layer.multihead_attn for layer in self.layers]
+        if memory_mask is None and memory_key_padding_mask is None and ops.kv_bank_applicable(memory, cross):
+            kv = ops.kv_bank(mem_key, memory, cross)
         output = tgt
         intermediate = []
-        for layer in self.layers:
+        for idx, layer in enumerate(self.layers):
             output, _ = layer(output, memory, tgt_mask=tgt_mask, memory_mask=memory_mask,
                               tgt_key_padding_mask=tgt_key_padding_mask,
                               memory_key_padding_mask=memory_key_padding_mask, pos=pos, query_pos=query_pos,
-                              memory_key=mem_key)
+                              memory_key=mem_key, kv_bank=None if kv is None else (kv[0], kv[1], idx))
             if self.return_intermediate:
                 intermediate.append(self.norm(output))
         if self.norm is not None:
@@ -313,9 +325,15 @@ class TransformerDecoderLayer(nn.Module):
     def with_pos_embed(tensor, pos: Optional[Tensor]):
         return tensor if pos is None else tensor + pos
 
+    def _cross(self, query, memory_key, memory, memory_mask, memory_key_padding_mask, kv_bank):
+        if kv_bank is not None:
+            return self.multihead_attn.forward_bank(query, *kv_bank)[0]
+        return self.multihead_attn(query, memory_key, memory, attn_mask=memory_mask,
+                                   key_padding_mask=memory_key_padding_mask)[0]
+
     def forward_pre(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
                     memory_key_padding_mask=None, pos=None, query_pos=None, return_attn_weights=False,
-                    memory_key=None):
+                    memory_key=None, kv_bank=None):
         # reference transformer.py:556-580
         if memory_key is None:
             memory_key = self.with_pos_embed(memory, pos)
@@ -324,8 +342,8 @@ class TransformerDecoderLayer(nn.Module):
         tgt2 = self.self_attn(qk, qk, tgt2, attn_mask=tgt_mask, key_padding_mask=tgt_key_padding_mask)[0]
         tgt = ops.dropout_add(tgt2, tgt, self.dropout1.p, self.training)
         tgt2 = self.norm2(tgt)
-        tgt2 = self.multihead_attn(self.with_pos_embed(tgt2, query_pos), memory_key, memory,
-                                   attn_mask=memory_mask, key_padding_mask=memory_key_padding_mask)[0]
+        tgt2 = self._cross(self.with_pos_embed(tgt2, query_pos), memory_key, memory, memory_mask,
+                           memory_key_padding_mask, kv_bank)
         tgt = ops.dropout_add(tgt2, tgt, self.dropout2.p, self.training)
         tgt2 = self.norm3(tgt)
         tgt2 = self.linear2(ops.dropout(_ffn_hidden(self, tgt2), self.dropout.p, self.training))
@@ -334,14 +352,14 @@ class TransformerDecoderLayer(nn.Module):
 
     def forward_post(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
                      memory_key_padding_mask=None, pos=None, query_pos=None, return_attn_weights=False,
-                     memory_key=None):
+                     memory_key=None, kv_bank=None):
         if memory_key is None:
             memory_key = self.with_pos_embed(memory, pos)
         qk = self.with_pos_embed(tgt, query_pos)
         tgt2 = self.self_attn(qk, qk, tgt, attn_mask=tgt_mask, key_padding_mask=tgt_key_padding_mask)[0]
         tgt = self.norm1(ops.dropout_add(tgt2, tgt, self.dropout1.p, self.training))
-        tgt2 = self.multihead_attn(self.with_pos_embed(tgt, query_pos), memory_key, memory,
-                                   attn_mask=memory_mask, key_padding_mask=memory_key_padding_mask)[0]
+        tgt2 = self._cross(self.with_pos_embed(tgt, query_pos), memory_key, memory, memory_mask,
+                           memory_key_padding_mask, kv_bank)
         tgt = self.norm2(ops.dropout_add(tgt2, tgt, self.dropout2.p, self.training))
         tgt2 = self.linear2(ops.dropout(_ffn_hidden(self, tgt), self.dropout.p, self.training))
         tgt = self.norm3(ops.dropout_add(tgt2, tgt, self.dropout3.p, self.training))
@@ -349,7 +367,7 @@ class TransformerDecoderLayer(nn.Module):
 
     def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
                 memory_key_padding_mask=None, pos=None, query_pos=None, return_attn_weights=False,
-                memory_key=None):
+                memory_key=None, kv_bank=None):
         fn = self.forward_pre if self.normalize_before else self.forward_post
         return fn(tgt, memory, tgt_mask, memory_mask, tgt_key_padding_mask, memory_key_padding_mask, pos,
-                  query_pos, return_attn_weights, memory_key)
+                  query_pos, return_attn_weights, memory_key, kv_bank)

@@ -964,3 +964,153 @@ class Linear(torch.nn.Linear):
 
     def forward(self, x):
         return linear(x, self.weight, self.bias)
+
+
+# --------------------------------------------------------------------------- decoder memory K / V bank
+def pack_weights_concat(ws, nsplit: int) -> torch.Tensor:
+    """Operand planes of the row-wise concatenation of the weights `ws` (each (n_i, k), row stride free):
+    (nsplit, 1, sum n_i, kpad) -- each weight is packed straight into its rows of the shared buffer."""
+    k = ws[0].shape[1]
+    kpad = _pad64(k)
+    total = sum(int(w.shape[0]) for w in ws)
+    out = torch.empty((nsplit, 1, total, kpad), dtype=torch.bfloat16, device=ws[0].device)
+    off = 0
+    with torch.cuda.device(out.device):
+        for w in ws:
+            wd = w.detach()
+            assert wd.dtype == torch.float32 and wd.stride(1) == 1 and wd.shape[1] == k
+            st = lib().coda_pack_split_bf16_strided(
+                _ll(wd.shape[0]), _i(k), _i(kpad), _ll(wd.stride(0)), _ll(1), ptr(wd), _f(1.0), _i(nsplit),
+                ctypes.c_void_p(out.data_ptr() + 2 * off * kpad), _ll(total * kpad), stream_of(wd))
+            check(st, "pack_split_bf16")
+            off += int(wd.shape[0])
+    return out
+
+
+class KVBank:
+    """Keys and values of the decoder's cross-attention for ALL layers at once.  The memory does not change across the
+    decoder layers (reference models/transformer.py:97-143: every layer projects the same `memory + pos` / `memory`
+    with its own weights), so the sixteen (16384 x 512 x 512) projections are two (16384 x 512 x 4096) GEMMs, and in the
+    backward the sixteen input-gradient GEMMs + fourteen full-size gradient accumulations on `memory` are two GEMMs
+    with a 4096-long contraction (the sum over layers happens in the tensor core's accumulator).
+
+    Autograd wiring: `_KVBankFn` returns a one-element TOKEN; each layer's cross-attention (`_AttentionBank`) takes the
+    token as a differentiable input and reads its K / V slice from the bank.  In the backward every attention node
+    writes its dK / dV slice into the bank's gradient buffers in place and returns a zero for the token, so autograd
+    runs `_KVBankFn.backward` exactly once, after the last layer that used the bank."""
+
+    def __init__(self):
+        self.k_all = self.v_all = self.dk_all = self.dv_all = None
+        self.nlayers = self.e = 0
+
+
+class _KVBankFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mem_key, memory, bank, nsplit, *params):
+        # params = (wk_0, bk_0, wv_0, bv_0, wk_1, ...): row slices of each layer's packed in-projection
+        nl = len(params) // 4
+        lk, b, e = memory.shape
+        xk = mem_key.reshape(lk * b, e)
+        xv = memory.reshape(lk * b, e)
+        if not a32_ok(xk):
+            xk = xk.contiguous()
+        if not a32_ok(xv):
+            xv = xv.contiguous()
+        wk, bk, wv, bv = params[0::4], params[1::4], params[2::4], params[3::4]
+        pk, pv = pack_weights_concat(wk, nsplit), pack_weights_concat(wv, nsplit)
+        bank.k_all = gemm_a32(xk, pk, nl * e, bias=torch.cat([t.detach() for t in bk]))
+        bank.v_all = gemm_a32(xv, pv, nl * e, bias=torch.cat([t.detach() for t in bv]))
+        bank.nlayers, bank.e = nl, e
+        bank.dk_all = bank.dv_all = None
+        ctx.bank, ctx.nsplit, ctx.shape = bank, nsplit, (lk, b, e)
+        ctx.save_for_backward(xk, xv, pk, pv, *params)
+        return torch.zeros(1, dtype=torch.float32, device=memory.device)
+
+    @staticmethod
+    def backward(ctx, dtoken):
+        bank = ctx.bank
+        xk, xv, pk, pv = ctx.saved_tensors[:4]
+        params = ctx.saved_tensors[4:]
+        lk, b, e = ctx.shape
+        nl = bank.nlayers
+        dk_all, dv_all = bank.dk_all, bank.dv_all
+        assert dk_all is not None and dv_all is not None, "no cross-attention used the K / V bank"
+        ns = min(ctx.nsplit, BACKWARD_NSPLIT)
+        d_key = d_mem = None
+        if ctx.needs_input_grad[0]:
+            d_key = gemm_a32(dk_all, pk, e, b_mn=True, nsplit=ns).view(lk, b, e)
+        if ctx.needs_input_grad[1]:
+            d_mem = gemm_a32(dv_all, pv, e, b_mn=True, nsplit=ns).view(lk, b, e)
+        grads = []
+        for i in range(nl):
+            for x, d_all, w, bias in ((xk, dk_all, params[4 * i], params[4 * i + 1]),
+                                      (xv, dv_all, params[4 * i + 2], params[4 * i + 3])):
+                dy = d_all[:, i * e: (i + 1) * e]                   # (rows, e) view, row stride nl * e
+                sw, sb = _sink(w), _sink(bias)
+                db = torch.empty(e, dtype=torch.float32, device=dy.device) if sb is None else sb
+                dw = gemm_tn32(dy, x, out=sw, colsum_out=db)
+                grads += [dw if sw is None else _sunk(sw), db if sb is None else _sunk(sb)]
+        bank.k_all = bank.v_all = bank.dk_all = bank.dv_all = None
+        return (d_key, d_mem, None, None, *grads)
+
+
+class _AttentionBank(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, token, bank, idx, nhead, dropout_p, salt):
+        from . import attention_launch
+
+        lk_b, ne = bank.k_all.shape
+        e = bank.e
+        lq, b, _ = q.shape
+        k = bank.k_all.view(lk_b // b, b, ne)[..., idx * e: (idx + 1) * e]
+        v = bank.v_all.view(lk_b // b, b, ne)[..., idx * e: (idx + 1) * e]
+        out, lse = attention_launch.forward(q, k, v, nhead, dropout_p, salt)
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.bank, ctx.idx, ctx.nhead, ctx.dropout_p, ctx.salt = bank, idx, nhead, dropout_p, salt
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import attention_launch
+
+        q, k, v, out, lse = ctx.saved_tensors
+        bank, idx, e = ctx.bank, ctx.idx, ctx.bank.e
+        lk, b, _ = k.shape
+        if bank.dk_all is None:          # every layer writes its own column block completely: no zero fill
+            bank.dk_all = torch.empty((lk * b, bank.nlayers * e), dtype=torch.float32, device=q.device)
+            bank.dv_all = torch.empty((lk * b, bank.nlayers * e), dtype=torch.float32, device=q.device)
+        dk = bank.dk_all.view(lk, b, -1)[..., idx * e: (idx + 1) * e]
+        dv = bank.dv_all.view(lk, b, -1)[..., idx * e: (idx + 1) * e]
+        dq = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+        attention_launch.backward(q, k, v, out, dout, lse, ctx.nhead, ctx.dropout_p, ctx.salt, grads=(dq, dk, dv))
+        return dq, torch.zeros(1, dtype=torch.float32, device=q.device), None, None, None, None, None
+
+
+def kv_bank(mem_key: torch.Tensor, memory: torch.Tensor, attn_modules, nsplit: int | None = None):
+    """-> (bank, token) for `attention_bank`; attn_modules: the layers' cross-attention modules (packed in_proj)"""
+    _need_cuda(memory, "kv_bank")
+    bank = KVBank()
+    params = []
+    for m in attn_modules:
+        e = m.embed_dim
+        w, bvec = m.in_proj_weight, m.in_proj_bias
+        params += [w[e: 2 * e], bvec[e: 2 * e], w[2 * e:], bvec[2 * e:]]
+    token = _KVBankFn.apply(mem_key, memory, bank, DEFAULT_NSPLIT if nsplit is None else nsplit, *params)
+    return bank, token
+
+
+def attention_bank(q: torch.Tensor, bank: KVBank, token: torch.Tensor, idx: int, nhead: int, dropout_p: float,
+                   training: bool) -> torch.Tensor:
+    from . import attention_launch
+
+    p = float(dropout_p) if training else 0.0
+    return _AttentionBank.apply(q, token, bank, idx, nhead, p, attention_launch.next_salt() if p > 0.0 else 0)
+
+
+def kv_bank_applicable(memory: torch.Tensor, attn_modules) -> bool:
+    if not (memory.is_cuda and memory.dtype == torch.float32 and len(attn_modules) > 1):
+        return False
+    e = attn_modules[0].embed_dim
+    hd = e // attn_modules[0].num_heads
+    return hd in (64, 128) and e % 64 == 0 and all(m.embed_dim == e and m.num_heads == attn_modules[0].num_heads
+                                                    for m in attn_modules)
