@@ -528,7 +528,10 @@ int coda_gemm_a32(int nsplit, int m, int n, int k, const float *a, long long lda
       (!a_argmax || a_group < 32 || a_group > 256 || m % a_group != 0 || k % 64 != 0 ||
        !(a_group % 128 == 0 || 128 % a_group == 0) || a_group % 32 != 0))
     return CODA_EINVAL;     // groups must tile the 128-row blocks (warp = 32 rows of one group)
-  const int bn = n <= 64 ? 64 : 128;
+  // few output tiles (the decoder's 2048-row linears: 16 x 4 tiles of 128 x 128 on 148 SMs): 64-wide tiles double
+  // the number of CTAs at work; each of these launches is bounded by one CTA's serial tile time, not by throughput
+  const long long tiles128 = (long long)((m + BM - 1) / BM) * ((n + 127) / 128);
+  const int bn = (n <= 64 || tiles128 <= num_sms() / 2) ? 64 : 128;
   A32Maps maps;
   int st = make_tmap_f32_box(&maps.a, a, k, m, lda, 32, BM);
   if (st != CODA_OK) return st;

@@ -32,6 +32,8 @@ def main():
              ("SA layer2 1Mx128x64 ns3 bn+relu prologue, stats epilogue", 1 << 20, 128, 64, 3, True, False),
              ("SA layer3 1Mx256x128 ns3 bn+relu prologue, stats epilogue", 1 << 20, 256, 128, 3, True, False),
              ("dX 16384x512x512 ns2 (MN-major W)", 16384, 512, 512, 2, False, True),
+             ("dX 2048x512x512 ns2 (MN-major W)", 2048, 512, 512, 2, False, True),
+             ("linear 2048x256x512 ns3 (decoder FFN1)", 2048, 256, 512, 3, False, False),
              ("SA dz1 1Mx128x256 ns2 (MN-major W)", 1 << 20, 128, 256, 2, False, True)]
     for name, m, n, k, ns, sa, mn in cases:
         if only and only not in name:
