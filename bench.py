@@ -269,7 +269,8 @@ def sa_wgrad_roofline(a, device):
     v = lambda c: (torch.rand(c, device=device) + 0.5, torch.randn(c, device=device) * 0.1)  # noqa: E731
     (sa, ta), (al, be), (sb, tb) = v(m), v(m), v(n)
     out = torch.empty(m, n, device=device)
-    ms = _time_launch(lambda: ops.gemm_tn32(y2, y1, a_mode=ops.A32_BN_BWD_POOLED, a_scale=sa, a_shift=ta, a_alpha=al,
+    # the step's form: the pooled gradient arrives masked and scaled (coda_bn_relu_bwd_reduce_pooled `dprime`)
+    ms = _time_launch(lambda: ops.gemm_tn32(y2, y1, a_mode=ops.A32_BN_BWD_POOLED_PRE, a_scale=sa, a_shift=ta, a_alpha=al,
                                             a_beta=be, a2=dp, argmax=arg, group=group, b_mode=ops.A32_AFFINE_RELU,
                                             b_scale=sb, b_shift=tb, out=out))
     nbytes = 4.0 * rows * (m + n) + 5.0 * (rows // group) * m + 4.0 * m * n

@@ -112,7 +112,7 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char *raw_ring = smem;
   const bool two_in = P.mode == CODA_A32_BN_BWD;
-  const bool pooled = P.mode == CODA_A32_BN_BWD_POOLED;
+  const bool pooled = P.mode == CODA_A32_BN_BWD_POOLED || P.mode == CODA_A32_BN_BWD_POOLED_PRE;
   // pooled BatchNorm backward: each raw stage carries, after the fp32 tile, the (group, channel) gradient and
   // arg-max rows of the tile's groups for this k-block: [groups in tile][64 floats | 64 bytes]  (<= 1 KB)
   const int raw_stage_bytes = RAW_TILE * (two_in ? 2 : 1) + (pooled ? 1024 : 0);
@@ -326,6 +326,21 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
               x[4 * j + 2] = (fmaf(x[4 * j + 2], s4.z, t4.z) > 0.f ? s4.z * d.z : 0.f) + fmaf(x[4 * j + 2], a4.z, b4.z);
               x[4 * j + 3] = (fmaf(x[4 * j + 3], s4.w, t4.w) > 0.f ? s4.w * d.w : 0.f) + fmaf(x[4 * j + 3], a4.w, b4.w);
             }
+          } else if (P.mode == CODA_A32_BN_BWD_POOLED_PRE) {
+            // pre-masked, pre-scaled pooled gradient: one compare + select + FMA + add per element
+            const int gi = pgi;
+            const unsigned char *px = rt + RAW_TILE + pgt * 320;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 a4 = __ldg(reinterpret_cast<const float4 *>(P.alpha + kc) + j);
+              const float4 b4 = __ldg(reinterpret_cast<const float4 *>(P.beta + kc) + j);
+              const float4 d = *reinterpret_cast<const float4 *>(px + (ch * 16 + 4 * j) * 4);
+              const uchar4 id = *reinterpret_cast<const uchar4 *>(px + 256 + ch * 16 + 4 * j);
+              x[4 * j] = (id.x == gi ? d.x : 0.f) + fmaf(x[4 * j], a4.x, b4.x);
+              x[4 * j + 1] = (id.y == gi ? d.y : 0.f) + fmaf(x[4 * j + 1], a4.y, b4.y);
+              x[4 * j + 2] = (id.z == gi ? d.z : 0.f) + fmaf(x[4 * j + 2], a4.z, b4.z);
+              x[4 * j + 3] = (id.w == gi ? d.w : 0.f) + fmaf(x[4 * j + 3], a4.w, b4.w);
+            }
           } else if (P.mode == CODA_A32_BN_BWD_POOLED) {
             // the layer output was max-pooled over `group` rows: only the arg-max row of a (group, channel)
             // carries the incoming gradient dpooled[g][c]
@@ -520,11 +535,11 @@ int coda_gemm_a32(int nsplit, int m, int n, int k, const float *a, long long lda
   if (m == 0 || n == 0) return CODA_OK;
   if (!a || !b_planes || !c || b_ld % 64 != 0 || (lda & 3) || (ldc & 3) || ((uintptr_t)a & 15) || ((uintptr_t)c & 15))
     return CODA_EINVAL;
-  if (a_mode < CODA_A32_PLAIN || a_mode > CODA_A32_BN_BWD_POOLED) return CODA_EINVAL;
+  if (a_mode < CODA_A32_PLAIN || a_mode > CODA_A32_BN_BWD_POOLED_PRE) return CODA_EINVAL;
   if (a_mode != CODA_A32_PLAIN && (!a_scale || !a_shift || (k & 3))) return CODA_EINVAL;
   if (a_mode >= CODA_A32_BN_BWD && (!a2 || !a_alpha || !a_beta || ((uintptr_t)a2 & 15))) return CODA_EINVAL;
   if (a_mode == CODA_A32_BN_BWD && (lda2 & 3)) return CODA_EINVAL;
-  if (a_mode == CODA_A32_BN_BWD_POOLED &&
+  if ((a_mode == CODA_A32_BN_BWD_POOLED || a_mode == CODA_A32_BN_BWD_POOLED_PRE) &&
       (!a_argmax || a_group < 32 || a_group > 256 || m % a_group != 0 || k % 64 != 0 ||
        !(a_group % 128 == 0 || 128 % a_group == 0) || a_group % 32 != 0))
     return CODA_EINVAL;     // groups must tile the 128-row blocks (warp = 32 rows of one group)

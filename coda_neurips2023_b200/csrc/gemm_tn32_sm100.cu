@@ -133,7 +133,7 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
 
   if (warp == 0) {
     // ===== TMA producer =====
-    const bool pooled = P.a_mode == CODA_A32_BN_BWD_POOLED;
+    const bool pooled = P.a_mode == CODA_A32_BN_BWD_POOLED || P.a_mode == CODA_A32_BN_BWD_POOLED_PRE;
     const uint32_t bytes = (uint32_t)(RAW_A * (two_in ? 2 : 1) + RAW_B + (pooled ? 640 : 0));
     const long long ngroups = pooled ? P.rows / P.group : 0;
     for (long long i = 0; i < nkb; ++i) {
@@ -218,7 +218,8 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
       unsigned char *pl = pl_ring + (size_t)ps * PL_STAGE;
       const long long r0 = (kb0 + i) * BKR;
       int rem0 = 0;
-      if (P.a_mode == CODA_A32_BN_BWD_POOLED) rem0 = (int)(r0 % P.group);    // the slab's first row within its group
+      if (P.a_mode == CODA_A32_BN_BWD_POOLED || P.a_mode == CODA_A32_BN_BWD_POOLED_PRE)
+        rem0 = (int)(r0 % P.group);    // the slab's first row within its group
       // ---- A slab
 #pragma unroll
       for (int j = 0; j < BKR / TW; ++j) {
@@ -233,6 +234,14 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
           o.y = (fmaf(y.y, sa.y, ta.y) > 0.f ? sa.y * d.y : 0.f) + fmaf(y.y, al.y, be.y);
           o.z = (fmaf(y.z, sa.z, ta.z) > 0.f ? sa.z * d.z : 0.f) + fmaf(y.z, al.z, be.z);
           o.w = (fmaf(y.w, sa.w, ta.w) > 0.f ? sa.w * d.w : 0.f) + fmaf(y.w, al.w, be.w);
+        } else if (P.a_mode == CODA_A32_BN_BWD_POOLED_PRE) {
+          const int gi = rem0 + r;
+          const float4 d = *reinterpret_cast<const float4 *>(raw + 2 * RAW_A + RAW_B + lane * 16);
+          const uchar4 id = *reinterpret_cast<const uchar4 *>(raw + 2 * RAW_A + RAW_B + 512 + lane * 4);
+          o.x = (id.x == gi ? d.x : 0.f) + fmaf(y.x, al.x, be.x);
+          o.y = (id.y == gi ? d.y : 0.f) + fmaf(y.y, al.y, be.y);
+          o.z = (id.z == gi ? d.z : 0.f) + fmaf(y.z, al.z, be.z);
+          o.w = (id.w == gi ? d.w : 0.f) + fmaf(y.w, al.w, be.w);
         } else if (P.a_mode == CODA_A32_BN_BWD_POOLED) {
           const int gi = rem0 + r;
           const float4 d = *reinterpret_cast<const float4 *>(raw + 2 * RAW_A + RAW_B + lane * 16);
@@ -378,11 +387,13 @@ int coda_gemm_tn32(long long rows, int m, int n, const float *a, long long lda, 
   if (rows <= 0 || m <= 0 || n <= 0 || !a || !b || !c) return CODA_EINVAL;
   if ((lda & 3) || (ldb & 3) || (ldc & 3) || (m & 3) || (n & 3)) return CODA_EINVAL;
   if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) return CODA_EINVAL;
-  if (a_mode != CODA_A32_PLAIN && a_mode != CODA_A32_BN_BWD && a_mode != CODA_A32_BN_BWD_POOLED) return CODA_EINVAL;
+  if (a_mode != CODA_A32_PLAIN && a_mode != CODA_A32_BN_BWD && a_mode != CODA_A32_BN_BWD_POOLED &&
+      a_mode != CODA_A32_BN_BWD_POOLED_PRE)
+    return CODA_EINVAL;
   if (b_mode != CODA_A32_PLAIN && b_mode != CODA_A32_AFFINE_RELU) return CODA_EINVAL;
   if (a_mode != CODA_A32_PLAIN && (!a_scale || !a_shift || !a_alpha || !a_beta || !a2 || ((uintptr_t)a2 & 15))) return CODA_EINVAL;
   if (a_mode == CODA_A32_BN_BWD && (lda2 & 3)) return CODA_EINVAL;
-  if (a_mode == CODA_A32_BN_BWD_POOLED &&
+  if ((a_mode == CODA_A32_BN_BWD_POOLED || a_mode == CODA_A32_BN_BWD_POOLED_PRE) &&
       (!a_argmax || a_group < 32 || a_group > 256 || a_group % 32 != 0 || rows % a_group != 0 || m % 128 != 0))
     return CODA_EINVAL;     // a 32-row slab must lie in one group; the group rows are staged 128 columns at a time
   if (b_mode == CODA_A32_AFFINE_RELU && (!b_scale || !b_shift)) return CODA_EINVAL;

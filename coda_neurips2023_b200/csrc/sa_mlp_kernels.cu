@@ -365,7 +365,7 @@ bn_relu_bwd_reduce_pooled_kernel(long long groups, int group, int c, const float
                                  const float *__restrict__ dpooled, const unsigned char *__restrict__ argmax,
                                  const float *__restrict__ mean, const float *__restrict__ invstd,
                                  const float *__restrict__ gamma, const float *__restrict__ beta,
-                                 float *__restrict__ partial) {
+                                 float *__restrict__ partial, float *__restrict__ dprime) {
   __shared__ float4 red[THREADS];
   const int cq = c >> 2, c4 = threadIdx.x % cq, slot = threadIdx.x / cq, nslots = THREADS / cq;
   const Affine4 a = load_affine(mean, invstd, gamma, beta, c4);
@@ -379,6 +379,10 @@ bn_relu_bwd_reduce_pooled_kernel(long long groups, int group, int c, const float
     const float4 z = bn4(xh, a);
     float4 d = __ldg(reinterpret_cast<const float4 *>(dpooled + g * c) + c4);
     d.x = z.x > 0.f ? d.x : 0.f; d.y = z.y > 0.f ? d.y : 0.f; d.z = z.z > 0.f ? d.z : 0.f; d.w = z.w > 0.f ? d.w : 0.f;
+    if (dprime)      // masked gradient times gamma * invstd: what the GEMM prologues add at the arg-max row
+      reinterpret_cast<float4 *>(dprime + g * c)[c4] =
+          make_float4(a.gamma.x * a.invstd.x * d.x, a.gamma.y * a.invstd.y * d.y, a.gamma.z * a.invstd.z * d.z,
+                      a.gamma.w * a.invstd.w * d.w);
     acc[0].x += d.x; acc[0].y += d.y; acc[0].z += d.z; acc[0].w += d.w;
     acc[1].x = fmaf(d.x, xh.x, acc[1].x); acc[1].y = fmaf(d.y, xh.y, acc[1].y);
     acc[1].z = fmaf(d.z, xh.z, acc[1].z); acc[1].w = fmaf(d.w, xh.w, acc[1].w);
@@ -643,14 +647,14 @@ int coda_bn_relu_bwd_reduce(long long rows, int c, const float *y, const float *
 int coda_bn_relu_bwd_reduce_pooled(long long groups, int group, int c, const float *y, const float *dpooled,
                                    const unsigned char *argmax, const float *mean, const float *invstd,
                                    const float *gamma, const float *beta, float *s1, float *s2, float *scratch,
-                                   void *stream) {
+                                   float *dprime, void *stream) {
   if (groups <= 0 || group < 1 || group > 256 || !channels_ok(c) || !y || !dpooled || !argmax || !mean || !invstd ||
       !gamma || !beta || !s1 || !s2 || !scratch)
     return CODA_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = grid_for(groups, c);
   bn_relu_bwd_reduce_pooled_kernel<<<grid, THREADS, 0, s>>>(groups, group, c, y, dpooled, argmax, mean, invstd, gamma,
-                                                           beta, scratch);
+                                                           beta, scratch, dprime);
   sums_finalize_kernel<<<(c + 7) / 8, 256, 0, s>>>((int)grid, c, scratch, s1, s2);
   return coda::launch_status();
 }

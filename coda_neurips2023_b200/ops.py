@@ -655,6 +655,7 @@ def gemm_nt(a_planes: torch.Tensor, b_planes: torch.Tensor, m: int, n: int, bias
 
 
 A32_PLAIN, A32_AFFINE_RELU, A32_BN_BWD, A32_BN_BWD_POOLED = 0, 1, 2, 3
+A32_BN_BWD_POOLED_PRE = 4     # a2 = pre-masked, pre-scaled pooled gradient (coda_bn_relu_bwd_reduce_pooled `dprime`)
 
 
 def a32_ok(a: torch.Tensor) -> bool:
@@ -687,7 +688,7 @@ def gemm_a32(a: torch.Tensor, b_planes: torch.Tensor, n: int, *, mode: int = A32
     if mode == A32_BN_BWD:
         assert a32_ok(a2) and a2.shape == a.shape
         lda2 = a2.stride(0)
-    elif mode == A32_BN_BWD_POOLED:
+    elif mode in (A32_BN_BWD_POOLED, A32_BN_BWD_POOLED_PRE):
         assert a2.is_contiguous() and argmax.is_contiguous() and a2.shape == (m // group, k)
     with torch.cuda.device(a.device):
         st = L.coda_gemm_a32(_i(ns), _i(m), _i(n), _i(k), ptr(a), _ll(a.stride(0)), _i(mode), ptr(scale), ptr(shift),
@@ -720,7 +721,7 @@ def gemm_tn32(a: torch.Tensor, b: torch.Tensor, *, a_mode: int = A32_PLAIN, a_sc
     if a_mode == A32_BN_BWD:
         assert a32_ok(a2) and a2.shape == a.shape
         lda2 = a2.stride(0)
-    elif a_mode == A32_BN_BWD_POOLED:
+    elif a_mode in (A32_BN_BWD_POOLED, A32_BN_BWD_POOLED_PRE):
         assert a2.is_contiguous() and argmax.is_contiguous() and a2.shape == (rows // group, m)
     with torch.cuda.device(a.device):
         st = lib().coda_gemm_tn32(_ll(rows), _i(m), _i(n), ptr(a), _ll(a.stride(0)), _i(a_mode), ptr(a_scale),

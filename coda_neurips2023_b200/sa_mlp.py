@@ -208,9 +208,12 @@ class _SharedMLPMax(torch.autograd.Function):
                 scratch = _scratch(cout, dev)
                 pooled_form = li == nl - 1
                 if pooled_form:
+                    # dprime: the pooled gradient already masked by the ReLU of its arg-max row and scaled by gamma *
+                    # invstd -- the GEMM prologues below only place it
+                    dprime = torch.empty_like(dpooled)
                     check(L.coda_bn_relu_bwd_reduce_pooled(_ll(rows // group), _i(group), _i(cout), ptr(y), ptr(dpooled),
                                                            ptr(argmax), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta),
-                                                           ptr(s1), ptr(s2), ptr(scratch), stream_of(x)),
+                                                           ptr(s1), ptr(s2), ptr(scratch), ptr(dprime), stream_of(x)),
                           "bn_relu_bwd_reduce_pooled")
                 else:
                     check(L.coda_bn_relu_bwd_reduce(_ll(rows), _i(cout), ptr(y), ptr(dz), ptr(mean), ptr(invstd),
@@ -252,7 +255,7 @@ class _SharedMLPMax(torch.autograd.Function):
                 pro = dict(a_scale=scales[li], a_shift=shifts[li], a_alpha=alpha, a_beta=bcoef)
                 if pooled_form and group % 32 == 0 and (128 % group == 0 or group % 128 == 0) and cout % 128 == 0:
                     # the arg-max rows / pooled gradient of a tile's groups travel with the raw tiles (TMA)
-                    mode, a2 = ops.A32_BN_BWD_POOLED, dpooled
+                    mode, a2 = ops.A32_BN_BWD_POOLED_PRE, dprime
                     extra = dict(argmax=argmax, group=group)
                 elif pooled_form:
                     # group sizes that do not tile the kernels' 32-row slabs: expand the pooled gradient once

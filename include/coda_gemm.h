@@ -99,6 +99,9 @@ int coda_gemm_tn(int nsplit, int mc, int m, int n, const void *a, long long a_pl
 #define CODA_A32_AFFINE_RELU 1
 #define CODA_A32_BN_BWD 2
 #define CODA_A32_BN_BWD_POOLED 3
+/* as _POOLED, but a2 already holds [bn(y) > 0 at the arg-max row] * scale * dpooled (coda_bn_relu_bwd_reduce_pooled's
+ * `dprime`): the prologue is  T = [argmax == row] * a2 + a * alpha + beta  -- no ReLU test, no multiply per element */
+#define CODA_A32_BN_BWD_POOLED_PRE 4
 int coda_gemm_a32_grid(int m, int n);
 int coda_gemm_a32(int nsplit, int m, int n, int k, const float *a, long long lda, int a_mode, const float *a_scale,
                   const float *a_shift, const float *a_alpha, const float *a_beta, const float *a2, long long lda2,

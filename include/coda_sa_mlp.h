@@ -109,7 +109,9 @@ int coda_bn_relu_maxpool_rows(long long groups, int group, int c, const float *y
  * Backward of relu(bn(y)) given the gradient of its output, first half: s1[c] = sum_r dz_masked,
  * s2[c] = sum_r dz_masked * xhat  (= dbeta, dgamma), dz_masked = dz where bn(y) > 0 else 0.
  *   dense form  : dz (rows, c);
- *   pooled form : the output was max-pooled; dpooled (groups, c) + argmax (groups, c) stand for dz.
+ *   pooled form : the output was max-pooled; dpooled (groups, c) + argmax (groups, c) stand for dz.  dprime
+ *                 (groups, c), or NULL: receives [bn(y) > 0 at the arg-max row] * gamma * invstd * dpooled, the operand
+ *                 of the CODA_A32_BN_BWD_POOLED_PRE prologue of coda_gemm_a32 / coda_gemm_tn32.
  */
 int coda_bn_relu_bwd_reduce(long long rows, int c, const float *y, const float *dz, const float *mean,
                             const float *invstd, const float *gamma, const float *beta, float *s1, float *s2,
@@ -117,7 +119,7 @@ int coda_bn_relu_bwd_reduce(long long rows, int c, const float *y, const float *
 int coda_bn_relu_bwd_reduce_pooled(long long groups, int group, int c, const float *y, const float *dpooled,
                                    const unsigned char *argmax, const float *mean, const float *invstd,
                                    const float *gamma, const float *beta, float *s1, float *s2, float *scratch,
-                                   void *stream);
+                                   float *dprime, void *stream);
 
 /*
  * Second half: dy = gamma * invstd * (dz_masked - s1 / rows - xhat * s2 / rows), written directly as the

@@ -101,6 +101,12 @@ def test_bn_backward_prologues():
     gotp = ops.gemm_a32(y, planes, n, mode=ops.A32_BN_BWD_POOLED, scale=scale, shift=shift, alpha=alpha, beta=beta,
                         a2=dp, argmax=arg, group=group, b_mn=True, nsplit=2)
     assert _rel(gotp, dyp @ w.double()) < 6e-5
+    # pre-masked, pre-scaled pooled gradient (what the step uses): the same values, fewer prologue instructions
+    zmax = torch.gather(z.view(m // group, group, k), 1, arg.long().unsqueeze(1)).squeeze(1)
+    dprime = ((zmax > 0) * scale.double() * dp.double()).float()
+    gotq = ops.gemm_a32(y, planes, n, mode=ops.A32_BN_BWD_POOLED_PRE, scale=scale, shift=shift, alpha=alpha, beta=beta,
+                        a2=dprime, argmax=arg, group=group, b_mn=True, nsplit=2)
+    assert _rel(gotq, dyp @ w.double()) < 6e-5
 
 
 @pytest.mark.parametrize("rows,m,n", [(65536, 256, 128), (10000, 128, 64), (4099, 512, 512), (700, 12, 512),
@@ -141,3 +147,8 @@ def test_tn32_bn_backward_and_forward_prologues():
     gotp = ops.gemm_tn32(y, yp, a_mode=ops.A32_BN_BWD_POOLED, a_scale=sa, a_shift=ta, a_alpha=al, a_beta=be, a2=dp,
                          argmax=arg, group=group, b_mode=ops.A32_AFFINE_RELU, b_scale=sb, b_shift=tb)
     assert _rel(gotp, dyp.t() @ x) < 6e-5
+    zmax = torch.gather(z.view(rows // group, group, m), 1, arg.long().unsqueeze(1)).squeeze(1)
+    dprime = ((zmax > 0) * sa.double() * dp.double()).float()
+    gotq = ops.gemm_tn32(y, yp, a_mode=ops.A32_BN_BWD_POOLED_PRE, a_scale=sa, a_shift=ta, a_alpha=al, a_beta=be,
+                         a2=dprime, argmax=arg, group=group, b_mode=ops.A32_AFFINE_RELU, b_scale=sb, b_shift=tb)
+    assert _rel(gotq, dyp.t() @ x) < 6e-5
