@@ -67,6 +67,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Wait for warps that are MANY and not on the critical path alone (GEMM transform / epilogue warps): a
+// three-instruction loop around try_wait with a suspend-time hint, so that a waiting warp sleeps in hardware instead
+// of spinning through select / compare / address-conversion instructions.  ncu on the weight-gradient GEMM: the spin
+// loops of the sixteen transform warps were a fifth of all issued instructions and took issue slots from the warps
+// that had work.  Single-warp roles (TMA producer, MMA issuer) keep the plain spin: lowest wake-up latency.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra DONE%=;\n\t"
+      "bra LAB_WAIT%=;\n\t"
+      "DONE%=:\n\t"
+      "}"
+      :
+      : "r"(addr), "r"(parity), "r"(0x989680u)
+      : "memory");
+}
 
 // Map a local shared-memory address to the same offset in CTA `rank` of the
 // cluster (shared::cluster window).

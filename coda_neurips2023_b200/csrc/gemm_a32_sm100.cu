@@ -280,8 +280,8 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
       }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int rs = it % nraw, as = it % A_STAGES;
-        mbar_wait(&raw_full[rs], (it / nraw) & 1u);
-        mbar_wait(&a_empty[as], ((it / A_STAGES) & 1u) ^ 1u);
+        mbar_wait_relaxed(&raw_full[rs], (it / nraw) & 1u);
+        mbar_wait_relaxed(&a_empty[as], ((it / A_STAGES) & 1u) ^ 1u);
         tc_fence_after();
         const unsigned char *rt = raw_ring + (size_t)rs * raw_stage_bytes;
         const uint32_t a_t = tmem_a0 + (uint32_t)as * A_COLS + lane_base;
@@ -399,7 +399,7 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
     for (long long t = 0; tile_at(t, m0, n0); ++t, ++tile_i) {
       const uint32_t buf = tile_i & 1u, use = tile_i >> 1;
       const int row = m0 + q * 32 + lane;
-      mbar_wait(&acc_full[buf], use & 1u);
+      mbar_wait_relaxed(&acc_full[buf], use & 1u);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + buf * ACC_COLS;
 #pragma unroll 1

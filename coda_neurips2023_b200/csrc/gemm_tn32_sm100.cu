@@ -210,16 +210,18 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
       tb = __ldg(reinterpret_cast<const float4 *>(P.b_shift + cb));
     }
     const bool a_col_ok = ca < P.m;
+    const bool pooled_mode = P.a_mode == CODA_A32_BN_BWD_POOLED || P.a_mode == CODA_A32_BN_BWD_POOLED_PRE;
+    // the slab's first row within its group, carried from slab to slab (group >= 32 = BKR: one conditional subtract)
+    int rem0 = pooled_mode ? (int)((kb0 * BKR) % P.group) : 0;
+    int rs = 0, ps = 0;
+    uint32_t raw_par = 0, pl_par = 1;
     for (long long i = 0; i < nkb; ++i) {
-      const int rs = (int)(i % RAW_STAGES), ps = (int)(i % PL_STAGES);
-      mbar_wait(&raw_full[rs], (uint32_t)((i / RAW_STAGES) & 1));
-      mbar_wait(&pl_empty[ps], (uint32_t)((i / PL_STAGES) & 1) ^ 1u);
+      mbar_wait_relaxed(&raw_full[rs], raw_par);
+      mbar_wait_relaxed(&pl_empty[ps], pl_par);
       const unsigned char *raw = raw_ring + (size_t)rs * RAW_STAGE;
       unsigned char *pl = pl_ring + (size_t)ps * PL_STAGE;
       const long long r0 = (kb0 + i) * BKR;
-      int rem0 = 0;
-      if (P.a_mode == CODA_A32_BN_BWD_POOLED || P.a_mode == CODA_A32_BN_BWD_POOLED_PRE)
-        rem0 = (int)(r0 % P.group);    // the slab's first row within its group
+      const bool tail = r0 + BKR > P.rows;         // only the very last slab can hold rows past the end
       // ---- A slab
 #pragma unroll
       for (int j = 0; j < BKR / TW; ++j) {
@@ -251,7 +253,7 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
           o.z = ((id.z == gi && fmaf(y.z, sa.z, ta.z) > 0.f) ? sa.z * d.z : 0.f) + fmaf(y.z, al.z, be.z);
           o.w = ((id.w == gi && fmaf(y.w, sa.w, ta.w) > 0.f) ? sa.w * d.w : 0.f) + fmaf(y.w, al.w, be.w);
         }
-        if (grow >= P.rows) o = make_float4(0.f, 0.f, 0.f, 0.f);     // padding rows of the last slab
+        if (tail && grow >= P.rows) o = make_float4(0.f, 0.f, 0.f, 0.f);     // padding rows of the last slab
         if (want_colsum) { csum.x += o.x; csum.y += o.y; csum.z += o.z; csum.w += o.w; }
         // destination: box = column / 64, 16-byte chunk = (column % 64) / 8 swizzled by the row, half = (column % 8) / 4
         const int col = lane * 4;
@@ -269,7 +271,7 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
           v.x = fmaxf(fmaf(v.x, sb.x, tb.x), 0.f); v.y = fmaxf(fmaf(v.y, sb.y, tb.y), 0.f);
           v.z = fmaxf(fmaf(v.z, sb.z, tb.z), 0.f); v.w = fmaxf(fmaf(v.w, sb.w, tb.w), 0.f);
         }
-        if (grow >= P.rows) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tail && grow >= P.rows) v = make_float4(0.f, 0.f, 0.f, 0.f);
         const int col = bch * 4;
         store_planes4(v, pl + NS * PL_A + (col >> 6) * (BKR * 128) + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) +
                              ((col & 7) >> 2) * 8,
@@ -281,6 +283,9 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
         mbar_arrive(&raw_empty[rs]);
         mbar_arrive(&pl_full[ps]);
       }
+      if (++rs == RAW_STAGES) { rs = 0; raw_par ^= 1u; }
+      if (++ps == PL_STAGES) { ps = 0; pl_par ^= 1u; }
+      if (pooled_mode) { rem0 += BKR; if (rem0 >= P.group) rem0 -= P.group; }
     }
     if (want_colsum && a_col_ok) {
       atomicAdd(&s_colsum[lane * 4], csum.x); atomicAdd(&s_colsum[lane * 4 + 1], csum.y);
@@ -293,7 +298,7 @@ gemm_tn32_kernel(const __grid_constant__ TN32Maps maps, const TN32Params P) {
     unsigned char *stage = epi + (size_t)q * (32 * 128);
     unsigned char *srow = stage + lane * 128;
     const int sw = lane & 7;
-    mbar_wait(&acc_full, 0);
+    mbar_wait_relaxed(&acc_full, 0);
     tc_fence_after();
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
