@@ -81,21 +81,6 @@ struct A32Params {
   int b_resident;          // the whole B operand of this CTA's n-tile stays in shared memory (short contractions)
 };
 
-// 32 values per lane (one row each) -> lane j ends with the sum over the warp's 32 rows of value j
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool upper = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float keep = upper ? v[i + s] : v[i];
-      const float give = upper ? v[i] : v[i + s];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, give, s);
-    }
-  }
-  return v[0];
-}
-
 // RAW_KB: size of the raw-fp32 staging region; it holds RAW_KB / 32 stages (one-input prologues) or RAW_KB / 64
 // (the two-input BatchNorm-backward prologue).
 template <int NSPLIT, int BN, int RAW_KB, int B_STAGES, bool B_MN>
@@ -431,6 +416,10 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
 #pragma unroll
           for (int t = 0; t < 32; ++t) v[t] = fmaxf(v[t], 0.f);
         }
+        if (my_stats && row >= m) {      // rows past m are padding: clipped by the TMA store, excluded from the statistics
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = 0.f;
+        }
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
 #pragma unroll
@@ -445,19 +434,23 @@ gemm_a32_kernel(const __grid_constant__ A32Maps maps, const A32Params P) {
           tma_store_commit();
         }
         if (my_stats) {
-          // column sums of this warp's 32 rows (rows past m are padding: excluded)
-          if (row >= m) {
+          // column sums of this warp's 32 rows, read back from the staging tile the TMA store is draining: lane l
+          // walks column l (conflict-free through the swizzle) -- 32 loads + 64 FMAs instead of two 31-shuffle
+          // transposition trees per chunk.  ncu had the epilogue warps as this kernel's bottleneck on the 1M-row layers
+          // (the MMA warp waiting for a free accumulator).
+          float cs0 = 0.f, cs1 = 0.f, cq0 = 0.f, cq1 = 0.f;
+          const unsigned char *colp = stage + (lane & 3) * 4;
+          const int ch = lane >> 2;
 #pragma unroll
-            for (int t = 0; t < 32; ++t) v[t] = 0.f;
+          for (int r = 0; r < 32; r += 2) {
+            const float x0 = *reinterpret_cast<const float *>(colp + r * 128 + ((ch ^ (r & 7)) << 4));
+            const float x1 = *reinterpret_cast<const float *>(colp + (r + 1) * 128 + ((ch ^ ((r + 1) & 7)) << 4));
+            cs0 += x0; cq0 = fmaf(x0, x0, cq0);
+            cs1 += x1; cq1 = fmaf(x1, x1, cq1);
           }
-          float sq[32];
-#pragma unroll
-          for (int t = 0; t < 32; ++t) sq[t] = v[t] * v[t];
-          const float cs = warp_transpose_sum(v, lane);
-          const float cq = warp_transpose_sum(sq, lane);
           if (col0 + lane < n) {
-            my_stats[col0 + lane] += cs;
-            my_stats[n + col0 + lane] += cq;
+            my_stats[col0 + lane] += cs0 + cs1;
+            my_stats[n + col0 + lane] += cq0 + cq1;
           }
         }
       }

@@ -34,7 +34,10 @@ CASES = {
                     dict(curr_epoch=540)),
     # `--enc_type masked` (reference models/transformer.py:146-211, model_3detr.py:3958-3980): radius-masked
     # self-attention (0.16 / 0.64 / 1.44) with the interim set-abstraction down-sampling after the first layer
-    "masked_small": (2, 3000, dict(_SMALL, enc_type="masked")),
+    # gradient bar 1e-2: at 256 seeds the 0.4 m / 0.8 m radius masks of the first two layers leave every point
+    # attending to itself only, so the q / k rows of their in-projection have a gradient that is zero in exact
+    # arithmetic -- what the check sees there is the two-plane rounding of the backward (measured 4.8e-3 .. 5.6e-3)
+    "masked_small": (2, 3000, dict(_SMALL, enc_type="masked"), dict(grad_rtol=1e-2)),
     # the configuration the BASELINE metric is quoted on: 2048 seeds, enc 3 x 256, dec 8 x 512, 256 queries,
     # 20 000 points (2 scenes so that the CPU reference run stays in minutes)
     "baseline_full": (2, 20000, dict(_NODROP)),
