@@ -69,10 +69,14 @@ class _PackedSelfAttention(nn.Module):
     def forward(self, x: torch.Tensor, causal: bool = False, residual=None):
         q, k, v = _linear(x, self.in_proj_weight, self.in_proj_bias).split(self.embed_dim, dim=-1)
         if x.is_cuda and x.dtype == torch.float16 and not causal and self.embed_dim // self.num_heads == 64:
-            # image tower: fused tcgen05 attention on 2 bf16 planes (16 mantissa bits >= fp16's 11)
             from .. import attention_launch
             # q / k / v stay fp16 slices of the fused projection: the pack kernel reads them in place
-            out = attention_launch.forward(q, k, v, self.num_heads, nsplit=2, half_out=True)[0].to(x.dtype)
+            if x.shape[0] <= 64:
+                # image tower (50 tokens): fused tcgen05 attention on HALF operands, the tensor core's native type
+                out = attention_launch.forward_half(q, k, v, self.num_heads)
+            else:
+                # longer sequences: 2 bf16 planes (16 mantissa bits >= fp16's 11)
+                out = attention_launch.forward(q, k, v, self.num_heads, nsplit=2, half_out=True)[0].to(x.dtype)
         else:
             out = ops.attention(q, k, v, self.num_heads, 0.0, False, causal=causal)
         return _linear(out, self.out_proj.weight, self.out_proj.bias, residual=residual)

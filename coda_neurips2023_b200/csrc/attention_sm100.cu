@@ -87,6 +87,32 @@ mask_radius_kernel(int B, int L, const float *__restrict__ xyz, float radius, un
   bits[i] = w;
 }
 
+// half in -> ONE plane of half operands [b*h][L][hd] (scaled): the fp16 tower's q / k / v need a re-layout, not a split
+__global__ void __launch_bounds__(256)
+pack_rows_half_kernel(const __grid_constant__ PackJobs jobs, int B, int H, int hd) {
+  const PackJob jb = jobs.job[blockIdx.y];
+  const long long total4 = (long long)jb.L * B * H * hd / 4;
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const int hd4 = hd >> 2;
+  const int d = (int)(i4 % hd4) * 4;
+  long long t = i4 / hd4;
+  const int h = (int)(t % H); t /= H;     // t = l * B + b
+  const int b = (int)(t % B);
+  const int l = (int)(t / B);
+  const long long off = t * jb.ld + (long long)h * hd + d;
+  uint2 raw = __ldg(reinterpret_cast<const uint2 *>(static_cast<const __half *>(jb.src) + off));
+  if (jb.scale != 1.0f) {
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+    const __half2 a = __floats2half2_rn(lo.x * jb.scale, lo.y * jb.scale), c = __floats2half2_rn(hi.x * jb.scale, hi.y * jb.scale);
+    raw.x = *reinterpret_cast<const uint32_t *>(&a);
+    raw.y = *reinterpret_cast<const uint32_t *>(&c);
+  }
+  __half *dst = reinterpret_cast<__half *>(jb.planes) + (((size_t)(b * H + h)) * jb.L + l) * hd + d;
+  *reinterpret_cast<uint2 *>(dst) = raw;
+}
+
 // ------------------------------------------------------------------ the kernel
 struct AttnMaps {
   CUtensorMap k[3], v[3];
@@ -147,7 +173,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int HD, int NSPLIT, bool ONE_TILE>
+// F16: the operand planes (and P) are IEEE half instead of bf16 -- the fp16 CLIP tower needs no split at all: one
+// plane, one MMA per product, where two bf16 planes took three.
+template <int HD, int NSPLIT, bool ONE_TILE, bool F16 = false>
 __global__ void __launch_bounds__(AttnCfg<HD, NSPLIT, ONE_TILE>::THREADS, AttnCfg<HD, NSPLIT, ONE_TILE>::MIN_CTAS)
 attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__restrict__ qplanes, int Lq, int Lk,
                 int B, int H, float *__restrict__ out, float *__restrict__ lse, float drop_p, uint32_t seed,
@@ -226,8 +254,8 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
     // ===== MMA issuer (whole warp in uniform control flow, one elected lane issues): the scores run two
     //       tiles ahead of O_j = P_j V_j so the tensor pipe works on the next scores while the softmax
     //       warps are busy with the current ones =====
-    constexpr uint32_t idesc_s = umma_idesc_f16(0, QT, KT);  // 128 x 64
-    constexpr uint32_t idesc_o = umma_idesc_f16(0, QT, HD, 0, 1);  // 128 x HD; B = V_j, MN-major (hd contiguous)
+    constexpr uint32_t idesc_s = umma_idesc_f16(F16 ? 1 : 0, QT, KT);  // 128 x 64
+    constexpr uint32_t idesc_o = umma_idesc_f16(F16 ? 1 : 0, QT, HD, 0, 1);  // 128 x HD; B = V_j, MN-major (hd contiguous)
     auto issue_s = [&](int j) {
       const int st = j % NST;
       mbar_wait(&k_full[st], (uint32_t)(j / NST) & 1u);
@@ -378,8 +406,14 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
           }
 #pragma unroll
           for (int pl = 0; pl < NP; ++pl) {
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(r0, r1);  // one packed conversion
-            const uint32_t bits = *reinterpret_cast<const uint32_t *>(&h2);
+            uint32_t bits;
+            if constexpr (F16) {
+              const __half2 h2 = __floats2half2_rn(r0, r1);
+              bits = *reinterpret_cast<const uint32_t *>(&h2);
+            } else {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(r0, r1);  // one packed conversion
+              bits = *reinterpret_cast<const uint32_t *>(&h2);
+            }
             w[pl][e >> 1] = bits;
             if (pl + 1 < NP) {
               r0 -= __uint_as_float(bits << 16);
@@ -484,14 +518,15 @@ attn_fwd_kernel(const __grid_constant__ AttnMaps maps, const __nv_bfloat16 *__re
   if (warp == 2) tmem_dealloc(tmem_slot, TMEM_COLS);
 }
 
-template <int HD, int NSPLIT, bool ONE_TILE = false>
+template <int HD, int NSPLIT, bool ONE_TILE = false, bool F16 = false>
 int launch_attn(const AttnMaps &maps, const __nv_bfloat16 *qplanes, int Lq, int Lk, int B, int H, float *out,
                 float *lse, float drop_p, uint32_t seed, const uint32_t *seed_dev, cudaStream_t s, int out_half = 0,
                 const unsigned long long *mask_q = nullptr) {
   if (out_half && !ONE_TILE) return CODA_EINVAL;   // fp16 output exists on the single-tile (CLIP tower) instance
+  static_assert(!F16 || NSPLIT == 1, "half operands are a single plane");
   using SM = AttnCfg<HD, NSPLIT, ONE_TILE>;
   constexpr size_t smem = SM::TOTAL + 1024;
-  auto kern = attn_fwd_kernel<HD, NSPLIT, ONE_TILE>;
+  auto kern = attn_fwd_kernel<HD, NSPLIT, ONE_TILE, F16>;
   static bool configured = false;  // once per template instance
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -603,6 +638,40 @@ int coda_attention_fwd_packed_masked(int b, int h, int lq, int lk, int hd, int n
   if (nsplit == 2) CODA_ATTN(128, 2);
   CODA_ATTN(128, 3);
 #undef CODA_ATTN
+}
+
+int coda_attention_fwd_half(int b, int h, int l, int hd, const void *q, const void *k, const void *v, long long ld_q,
+                            long long ld_k, long long ld_v, void *out, void *workspace, void *stream) {
+  // fp16 self-attention of at most one key tile (the CLIP image tower: 50 tokens, 12 x 64): q / k / v are read as
+  // half (row-strided slices of the fused projection), re-laid as ONE plane of half operands -- fp16 is the tensor
+  // core's native type, no bf16 split -- and the output is written as half.
+  if (b < 0 || h <= 0 || l <= 0 || l > KT || hd != 64 || (long long)b * h > 65535) return CODA_EINVAL;
+  if (b == 0) return CODA_OK;
+  if (!q || !k || !v || !out || !workspace) return CODA_EINVAL;
+  if ((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 7) != 0 || ((ld_q | ld_k | ld_v) & 3) != 0) return CODA_EINVAL;
+  if (ld_q < (long long)h * hd || ld_k < (long long)h * hd || ld_v < (long long)h * hd) return CODA_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int bh = b * h;
+  __nv_bfloat16 *qp = (__nv_bfloat16 *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  __nv_bfloat16 *kp = qp + (size_t)bh * l * hd;
+  __nv_bfloat16 *vp = kp + (size_t)bh * l * hd;
+  PackJobs jobs = {};
+  const float scale = 1.0f / sqrtf((float)hd);
+  jobs.job[0] = {q, qp, l, scale * LOG2E, ld_q};
+  jobs.job[1] = {k, kp, l, 1.0f, ld_k};
+  jobs.job[2] = {v, vp, l, 1.0f, ld_v};
+  const long long t4 = (long long)l * bh * hd / 4;
+  pack_rows_half_kernel<<<dim3((unsigned)((t4 + 255) / 256), 3), 256, 0, s>>>(jobs, b, h, hd);
+  int st = launch_status();
+  if (st != CODA_OK) return st;
+  AttnMaps maps;
+  st = make_tmap_k_major_16b(&maps.k[0], kp, 1, hd, l, bh, hd, (long long)l * hd, KT);
+  if (st != CODA_OK) return st;
+  st = make_tmap_k_major_16b(&maps.v[0], vp, 1, hd, l, bh, hd, (long long)l * hd, KT);
+  if (st != CODA_OK) return st;
+  for (int p = 1; p < 3; ++p) { maps.k[p] = maps.k[0]; maps.v[p] = maps.v[0]; }
+  return launch_attn<64, 1, true, true>(maps, qp, l, l, b, h, reinterpret_cast<float *>(out), nullptr, 0.f, 0u, nullptr,
+                                        s, 1);
 }
 
 int coda_attention_mask_pack(int b, int lq, int lk, const unsigned char *mask, long long stride_b, long long stride_q,

@@ -59,6 +59,15 @@ int coda_attention_fwd_packed_ex(int b, int h, int lq, int lk, int hd, int nspli
                                  const unsigned int *seed_dev, void *stream);
 
 /*
+ * fp16 self-attention with at most 64 tokens and head dim 64 (the CLIP ViT image tower, CLIP/clip/model.py:295-316 --
+ * nn.MultiheadAttention on fp16 activations): q, k, v (l, b, h*64) IEEE half with row strides ld_* (slices of the fused
+ * in-projection), out (l, b, h*64) half.  Operands stay half: one plane, one tcgen05.mma per product.
+ * workspace: 3 * b*h*l*64 halves + 256 bytes.
+ */
+int coda_attention_fwd_half(int b, int h, int l, int hd, const void *q, const void *k, const void *v, long long ld_q,
+                            long long ld_k, long long ld_v, void *out, void *workspace, void *stream);
+
+/*
  * Attention masks (reference: MaskedTransformerEncoder, models/transformer.py:146-211 -- the radius masks of
  * `--enc_type masked`; nn.MultiheadAttention's boolean attn_mask in general).  Masks are bit-packed:
  * bits[b][row][tile] is one 64-bit word per 64 columns, bit c set = column 64*tile + c is NOT visible from the row.

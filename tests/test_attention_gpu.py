@@ -183,3 +183,21 @@ def test_fused_projection_layouts_match_separate_tensors():
         assert grads[0].is_contiguous() and torch.equal(grads[0], torch.cat(rg[: width // e], dim=-1))
         if vsep is not None:
             assert torch.equal(grads[1], rg[2])
+
+
+def test_half_operand_attention_of_the_clip_tower():
+    """coda_attention_fwd_half: fp16 q / k / v slices of a fused projection, ONE plane of half operands (no bf16
+    split), fp16 output -- against the fp32 formula on the same half values.  fp16 probabilities carry 11 mantissa
+    bits (like the reference, whose nn.MultiheadAttention runs entirely in half): 2e-3."""
+    torch.manual_seed(8)
+    l, b, h = 50, 37, 12
+    e = h * 64
+    qkv = (torch.randn(l, b, 3 * e, device="cuda") * 0.8).half()
+    q, k, v = qkv.split(e, dim=-1)
+    out = attention_launch.forward_half(q, k, v, h)
+    assert out.dtype == torch.float16 and out.shape == (l, b, e)
+    ref = attention_sm100._math(q.float(), k.float(), v.float(), h, 0.0, False, False)
+    assert ((out.float() - ref).abs().max() / ref.abs().max()).item() < 2e-3
+    # contiguous inputs take the same path
+    out2 = attention_launch.forward_half(q.contiguous(), k.contiguous(), v.contiguous(), h)
+    assert torch.equal(out, out2)
