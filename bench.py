@@ -192,7 +192,9 @@ def attention_roofline(a, device):
     v = torch.randn(lk, b, h * hd, device=device)
     L = _lib.lib()
     L.coda_attention_workspace_bytes.restype = ctypes.c_longlong
-    ns = a.nsplit
+    from coda_neurips2023_b200 import attention_launch
+
+    ns = attention_launch.FORWARD_NSPLIT      # the split the step's attention forward actually runs on
     ws = torch.empty(int(L.coda_attention_workspace_bytes(b, h, lq, lk, hd, ns)), dtype=torch.uint8, device=device)
     out = torch.empty_like(q)
     lse = torch.empty(b * h, lq, device=device)
@@ -242,6 +244,12 @@ def _time_launch(fn, reps=20, warm=3):
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
+
+
+def _attn_split():
+    from coda_neurips2023_b200 import attention_launch
+
+    return attention_launch.FORWARD_NSPLIT
 
 
 def _peaks():
@@ -429,7 +437,8 @@ def run_ours(a):
         "gpu_launches": launches, "gpu_launches_note": "C-ABI kernel-launching calls into libcoda_b200.so inside the "
                                                         "timed region (cuBLAS/cuDNN launches of torch not counted)",
         "clocks": clocks, "final_loss": lv, "cuda_graph": use_graph, "cuda_graph_note": graph_note,
-        "operand_split": a.nsplit, "param_spread_across_ranks": param_spread,
+        "operand_split": a.nsplit, "attention_forward_operand_split": _attn_split(),
+        "param_spread_across_ranks": param_spread,
         "grad_allreduce_bytes": step.flat.nbytes(),
     }
     line["roofline"] = sa_wgrad_roofline(a, device)

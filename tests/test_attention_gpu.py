@@ -45,7 +45,7 @@ def test_attention_dropout_mask_matches_torch_twin():
     lq, lk, b, h, hd = 256, 320, 2, 4, 64
     q, k, v = (torch.randn(n, b, h * hd, device="cuda") for n in (lq, lk, lk))
     attention_launch.seed_counter(q.device).fill_(12345)
-    out, _ = attention_launch.forward(q, k, v, h, dropout_p=0.1, salt=777)
+    out, _ = attention_launch.forward(q, k, v, h, dropout_p=0.1, salt=777, nsplit=3)
     keep = attention_launch.dropout_keep(b * h, lq, lk, 0.1, 777, q.device)
     assert 0.88 < keep.float().mean().item() < 0.92
     mult = attention_launch.dropout_mult(b * h, lq, lk, 0.1, 777, q.device)
@@ -58,9 +58,9 @@ def test_attention_autograd_wrapper():
     torch.manual_seed(1)
     lq, lk, b, h, hd = 200, 300, 2, 4, 64
     q, k, v = (torch.randn(n, b, h * hd, device="cuda", requires_grad=True) for n in (lq, lk, lk))
-    out = attention_sm100.attention(q, k, v, h)
+    out = attention_sm100.attention(q, k, v, h)          # the step's default: two operand planes in the forward
     ref = attention_sm100._math(q, k, v, h, 0.0, False, False)
-    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-5)
     g = torch.randn_like(out)
     got = torch.autograd.grad(out, (q, k, v), g)
     exp = torch.autograd.grad(ref, (q, k, v), g)
@@ -82,7 +82,7 @@ def test_attention_backward_vs_fp64(lq, lk, b, h, hd, p):
     k = (torch.randn(lk, b, e, device="cuda") * 1.2).requires_grad_(True)
     v = torch.randn(lk, b, e, device="cuda", requires_grad=True)
     attention_launch.seed_counter(q.device).fill_(4242)
-    out, lse = attention_launch.forward(q.detach(), k.detach(), v.detach(), h, dropout_p=p, salt=99)
+    out, lse = attention_launch.forward(q.detach(), k.detach(), v.detach(), h, dropout_p=p, salt=99, nsplit=3)
     g = torch.randn_like(out)
     dq, dk, dv = attention_launch.backward(q.detach(), k.detach(), v.detach(), out, g, lse, h, p, 99)
     keep = attention_launch.dropout_keep(b * h, lq, lk, p, 99, q.device) if p > 0 else None
@@ -134,7 +134,7 @@ def test_masked_attention_forward_backward_vs_fp64(lq, lk, b, h, hd, p):
     mask[:, :, lk - 1] = False                                 # every row keeps at least one key
     bits = attention_launch.mask_bits(mask, b)
     attention_launch.seed_counter(q.device).fill_(77)
-    out, lse = attention_launch.forward(q, k, v, h, dropout_p=p, salt=5, mask=bits)
+    out, lse = attention_launch.forward(q, k, v, h, dropout_p=p, salt=5, mask=bits, nsplit=3)
     g = torch.randn_like(out)
     dq, dk, dv = attention_launch.backward(q, k, v, out, g, lse, h, p, 5, mask=bits)
     keep = attention_launch.dropout_keep(b * h, lq, lk, p, 5, q.device) if p > 0 else None
@@ -201,3 +201,19 @@ def test_half_operand_attention_of_the_clip_tower():
     # contiguous inputs take the same path
     out2 = attention_launch.forward_half(q.contiguous(), k.contiguous(), v.contiguous(), h)
     assert torch.equal(out, out2)
+
+
+def test_default_forward_split_is_two_planes_and_meets_1e4():
+    """attention_launch.FORWARD_NSPLIT (2 unless CODA_ATTN_NSPLIT overrides it): the default call equals the explicit
+    two-plane call bit for bit and sits within 1e-4 of the fp64 formula on the encoder and decoder shapes."""
+    torch.manual_seed(11)
+    for lq, lk, b, h, hd in ((2048, 2048, 1, 4, 64), (256, 2048, 2, 4, 128)):
+        e = h * hd
+        q = torch.randn(lq, b, e, device="cuda") * 1.5
+        k = torch.randn(lk, b, e, device="cuda") * 1.5
+        v = torch.randn(lk, b, e, device="cuda")
+        out, _ = attention_launch.forward(q, k, v, h)
+        if attention_launch.FORWARD_NSPLIT == 2:
+            assert torch.equal(out, attention_launch.forward(q, k, v, h, nsplit=2)[0])
+        ref = _ref64(q, k, v, h)
+        assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 1e-4
