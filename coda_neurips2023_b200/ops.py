@@ -1087,6 +1087,13 @@ class _AttentionBank(torch.autograd.Function):
         return dq, torch.zeros(1, dtype=torch.float32, device=q.device), None, None, None, None, None
 
 
+def attention_operand_planes() -> int:
+    """bf16 planes on which the fused attention consumes q / k / v in the forward (and its producers compute them)"""
+    from . import attention_launch
+
+    return min(DEFAULT_NSPLIT, max(attention_launch.FORWARD_NSPLIT, BACKWARD_NSPLIT))
+
+
 def kv_bank(mem_key: torch.Tensor, memory: torch.Tensor, attn_modules, nsplit: int | None = None):
     """-> (bank, token) for `attention_bank`; attn_modules: the layers' cross-attention modules (packed in_proj)"""
     _need_cuda(memory, "kv_bank")
@@ -1096,7 +1103,11 @@ def kv_bank(mem_key: torch.Tensor, memory: torch.Tensor, attn_modules, nsplit: i
         e = m.embed_dim
         w, bvec = m.in_proj_weight, m.in_proj_bias
         params += [w[e: 2 * e], bvec[e: 2 * e], w[2 * e:], bvec[2 * e:]]
-    token = _KVBankFn.apply(mem_key, memory, bank, DEFAULT_NSPLIT if nsplit is None else nsplit, *params)
+    # the attention kernels consume K / V on attention_launch.FORWARD_NSPLIT planes: projecting them more precisely
+    # than that is work whose result the consumer rounds away
+    if nsplit is None:
+        nsplit = attention_operand_planes()
+    token = _KVBankFn.apply(mem_key, memory, bank, nsplit, *params)
     return bank, token
 
 
