@@ -59,37 +59,3 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=90, max_name_column_width=70))
 
-if "--stacks" in sys.argv:
-    # where do the remaining ATen kernels come from?  forward ops carry their Python stack; backward nodes of ATen
-    # ops are attributed to the forward call through the autograd sequence number
-    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], with_stack=True) as prof:
-        step(batch, 0.0)
-        torch.cuda.synchronize()
-    pkg = str(ROOT / "coda_neurips2023_b200")
-
-    def site(stack):
-        for fr in stack or []:
-            if pkg in fr:
-                return fr.replace(str(ROOT) + "/", "")
-        return None
-
-    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CPU]
-    fwd_site = {}
-    for e in evs:
-        s = site(e.stack)
-        if s and e.sequence_nr >= 0 and e.sequence_nr not in fwd_site:
-            fwd_site[e.sequence_nr] = s
-    agg = {}
-    for e in evs:
-        if not e.name.startswith("aten::") or e.self_device_time_total <= 0:
-            continue
-        s = site(e.stack)
-        if s is None and e.sequence_nr >= 0:
-            s = "bwd of " + fwd_site.get(e.sequence_nr, "?")
-        k = (e.name, s or "?")
-        a = agg.setdefault(k, [0.0, 0])
-        a[0] += e.self_device_time_total
-        a[1] += 1
-    print("ATen self-CUDA time by call site (us, launches):")
-    for (name, s), (us, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:70]:
-        print(f"{us:9.1f} {n:4d}  {name:28s} {s}")
