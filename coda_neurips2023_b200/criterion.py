@@ -201,6 +201,10 @@ class SetCriterion(nn.Module):
         pred = outputs["text_correlation_embedding"]
         pred = pred.reshape(self._nlayers, *target.shape)
         ave_weight = torch.sum(w) * pred.shape[-1]
+        if (pred.is_cuda and pred.shape[-1] % 4 == 0 and not target.requires_grad and not w.requires_grad
+                and w.numel() * pred.shape[-1] == target.numel()):
+            # |pred * w - target * w| summed per layer in one pass (and one pass backward): ops.masked_l1
+            return {"loss_predicted_region_embed_l1": ops.masked_l1(pred, target, w) / ave_weight}
         diff = (pred * w - target * w).abs()
         return {"loss_predicted_region_embed_l1": diff.sum(dim=(1, 2, 3)) / ave_weight}
 

@@ -29,11 +29,24 @@ __device__ __forceinline__ float warp_max(float v) {
 // =====================================================================
 constexpr int LN_WARPS = 8;
 
+// Where row r of a (rows, c) operand lives: r * c when inner == 0, else (r / inner) * so + (r % inner) * si floats --
+// a (q, b) -> (b, q) row permutation or a slice of a larger buffer costs no copy.
+struct RowMap {
+  int inner;
+  long long so, si;
+};
+__device__ __forceinline__ long long map_row(const RowMap &m, long long r, int c) {
+  return m.inner ? (r / m.inner) * m.so + (r % m.inner) * m.si : r * c;
+}
+
+// y = LayerNorm(x) (optional, row-mapped); ypos = y + pos (optional): the `norm(x) + query_pos` operand of the
+// decoder's attention comes out of the same pass.
 template <int NV>  // c == NV * 128
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layer_norm_fwd_kernel(long long rows, float eps, const float *__restrict__ x,
                       const float *__restrict__ gamma, const float *__restrict__ beta,
-                      float *__restrict__ y, float *__restrict__ mean_out,
+                      float *__restrict__ y, const RowMap ymap, const float *__restrict__ pos,
+                      float *__restrict__ ypos, float *__restrict__ mean_out,
                       float *__restrict__ rstd_out) {
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31;
@@ -56,7 +69,9 @@ layer_norm_fwd_kernel(long long rows, float eps, const float *__restrict__ x,
   }
   const float var = warp_sum(q) * (1.0f / C);
   const float rstd = 1.0f / sqrtf(var + eps);
-  float4 *yr = reinterpret_cast<float4 *>(y + row * C);
+  float4 *yr = y ? reinterpret_cast<float4 *>(y + map_row(ymap, row, C)) : nullptr;
+  const float4 *pr = pos ? reinterpret_cast<const float4 *>(pos + row * C) : nullptr;
+  float4 *ypr = pos ? reinterpret_cast<float4 *>(ypos + row * C) : nullptr;
   const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
   const float4 *b4 = reinterpret_cast<const float4 *>(beta);
 #pragma unroll
@@ -67,7 +82,11 @@ layer_norm_fwd_kernel(long long rows, float eps, const float *__restrict__ x,
     o.y = (v[i].y - mean) * rstd * g.y + b.y;
     o.z = (v[i].z - mean) * rstd * g.z + b.z;
     o.w = (v[i].w - mean) * rstd * g.w + b.w;
-    yr[lane + i * 32] = o;
+    if (yr) yr[lane + i * 32] = o;
+    if (pr) {
+      const float4 pv = __ldg(pr + lane + i * 32);
+      ypr[lane + i * 32] = make_float4(o.x + pv.x, o.y + pv.y, o.z + pv.z, o.w + pv.w);
+    }
   }
   if (lane == 0) {
     if (mean_out) mean_out[row] = mean;
@@ -121,9 +140,13 @@ layer_norm_fwd_half_kernel(long long rows, float eps, const __half *__restrict__
 
 constexpr int LN_BWD_ROWS_PER_BLOCK = 64;  // each warp walks 8 rows
 
+// d = dy (row-mapped) + dy2 (optional: the gradient that arrived through the `+ pos` output);
+// dx = LayerNormBackward(d) + add (optional: the gradient of the residual branch that by-passes the norm)
 template <int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-layer_norm_bwd_kernel(long long rows, const float *__restrict__ dy, const float *__restrict__ x,
+layer_norm_bwd_kernel(long long rows, const float *__restrict__ dy, const RowMap dmap,
+                      const float *__restrict__ dy2, const float *__restrict__ add,
+                      const float *__restrict__ x,
                       const float *__restrict__ gamma, const float *__restrict__ mean,
                       const float *__restrict__ rstd, float *__restrict__ dx,
                       float *__restrict__ partial) {
@@ -144,13 +167,19 @@ layer_norm_bwd_kernel(long long rows, const float *__restrict__ dy, const float 
     if (row >= rows) break;
     const float m = __ldg(mean + row), rs = __ldg(rstd + row);
     const float4 *xr = reinterpret_cast<const float4 *>(x + row * C);
-    const float4 *dr = reinterpret_cast<const float4 *>(dy + row * C);
+    const float4 *dr = reinterpret_cast<const float4 *>(dy + map_row(dmap, row, C));
+    const float4 *d2r = dy2 ? reinterpret_cast<const float4 *>(dy2 + row * C) : nullptr;
+    const float4 *ar = add ? reinterpret_cast<const float4 *>(add + row * C) : nullptr;
     float4 xh[NV], d[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const float4 xv = __ldg(xr + lane + i * 32);
       d[i] = __ldg(dr + lane + i * 32);
+      if (d2r) {
+        const float4 t = __ldg(d2r + lane + i * 32);
+        d[i].x += t.x; d[i].y += t.y; d[i].z += t.z; d[i].w += t.w;
+      }
       xh[i] = make_float4((xv.x - m) * rs, (xv.y - m) * rs, (xv.z - m) * rs, (xv.w - m) * rs);
       dg[i].x += d[i].x * xh[i].x; dg[i].y += d[i].y * xh[i].y;
       dg[i].z += d[i].z * xh[i].z; dg[i].w += d[i].w * xh[i].w;
@@ -168,6 +197,10 @@ layer_norm_bwd_kernel(long long rows, const float *__restrict__ dy, const float 
       o.y = rs * (d[i].y - c1 - xh[i].y * c2);
       o.z = rs * (d[i].z - c1 - xh[i].z * c2);
       o.w = rs * (d[i].w - c1 - xh[i].w * c2);
+      if (ar) {
+        const float4 t = __ldg(ar + lane + i * 32);
+        o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+      }
       dxr[lane + i * 32] = o;
     }
   }
@@ -516,21 +549,31 @@ hungarian_kernel(int nprop, int ngt, int stage_cost, const float *__restrict__ c
 // =====================================================================
 extern "C" {
 
-int coda_layer_norm_fwd(long long rows, int c, float eps, const float *x, const float *gamma,
-                        const float *beta, float *y, float *mean, float *rstd, void *stream) {
+int coda_layer_norm_fwd_ex(long long rows, int c, float eps, const float *x, const float *gamma,
+                           const float *beta, float *y, int y_inner, long long y_so, long long y_si,
+                           const float *pos, float *y_pos, float *mean, float *rstd, void *stream) {
   if (rows < 0 || c <= 0 || c % 128 != 0 || c > 1024) return CODA_EINVAL;
   if (rows == 0) return CODA_OK;
-  if (!x || !gamma || !beta || !y) return CODA_EINVAL;
+  if (!x || !gamma || !beta || (!y && !y_pos) || ((pos == nullptr) != (y_pos == nullptr))) return CODA_EINVAL;
+  if (y_inner < 0 || (y_inner > 0 && ((y_so & 3) || (y_si & 3)))) return CODA_EINVAL;
+  const RowMap ymap{y_inner, y_so, y_si};
   const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
   cudaStream_t s = (cudaStream_t)stream;
 #define CODA_LN_FWD(NV) \
-  case NV: layer_norm_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, s>>>(rows, eps, x, gamma, beta, y, mean, rstd); break;
+  case NV: layer_norm_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, s>>>(rows, eps, x, gamma, beta, y, ymap, pos, y_pos, \
+                                                                     mean, rstd); break;
   switch (c / 128) {
     CODA_LN_FWD(1) CODA_LN_FWD(2) CODA_LN_FWD(3) CODA_LN_FWD(4)
     CODA_LN_FWD(5) CODA_LN_FWD(6) CODA_LN_FWD(7) CODA_LN_FWD(8)
   }
 #undef CODA_LN_FWD
   return launch_status();
+}
+
+int coda_layer_norm_fwd(long long rows, int c, float eps, const float *x, const float *gamma,
+                        const float *beta, float *y, float *mean, float *rstd, void *stream) {
+  if (!y) return rows == 0 ? CODA_OK : CODA_EINVAL;
+  return coda_layer_norm_fwd_ex(rows, c, eps, x, gamma, beta, y, 0, 0, 0, nullptr, nullptr, mean, rstd, stream);
 }
 
 int coda_layer_norm_fwd_half(long long rows, int c, float eps, const void *x, const float *gamma,
@@ -556,9 +599,10 @@ long long coda_layer_norm_bwd_scratch(long long rows, int c) {
   return nblk * 2 * c;
 }
 
-int coda_layer_norm_bwd(long long rows, int c, const float *dy, const float *x, const float *gamma,
-                        const float *mean, const float *rstd, float *dx, float *dgamma,
-                        float *dbeta, float *partial, void *stream) {
+int coda_layer_norm_bwd_ex(long long rows, int c, const float *dy, int dy_inner, long long dy_so, long long dy_si,
+                           const float *dy2, const float *add, const float *x, const float *gamma,
+                           const float *mean, const float *rstd, float *dx, float *dgamma,
+                           float *dbeta, float *partial, void *stream) {
   if (rows < 0 || c <= 0 || c % 128 != 0 || c > 1024) return CODA_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
   if (rows == 0) {
@@ -567,9 +611,12 @@ int coda_layer_norm_bwd(long long rows, int c, const float *dy, const float *x, 
     return launch_status();
   }
   if (!dy || !x || !gamma || !mean || !rstd || !dx || !dgamma || !dbeta || !partial) return CODA_EINVAL;
+  if (dy_inner < 0 || (dy_inner > 0 && ((dy_so & 3) || (dy_si & 3)))) return CODA_EINVAL;
+  const RowMap dmap{dy_inner, dy_so, dy_si};
   const int nblk = (int)((rows + LN_BWD_ROWS_PER_BLOCK - 1) / LN_BWD_ROWS_PER_BLOCK);
 #define CODA_LN_BWD(NV) \
-  case NV: layer_norm_bwd_kernel<NV><<<nblk, LN_WARPS * 32, 0, s>>>(rows, dy, x, gamma, mean, rstd, dx, partial); break;
+  case NV: layer_norm_bwd_kernel<NV><<<nblk, LN_WARPS * 32, 0, s>>>(rows, dy, dmap, dy2, add, x, gamma, mean, rstd, \
+                                                                    dx, partial); break;
   switch (c / 128) {
     CODA_LN_BWD(1) CODA_LN_BWD(2) CODA_LN_BWD(3) CODA_LN_BWD(4)
     CODA_LN_BWD(5) CODA_LN_BWD(6) CODA_LN_BWD(7) CODA_LN_BWD(8)
@@ -579,6 +626,13 @@ int coda_layer_norm_bwd(long long rows, int c, const float *dy, const float *x, 
   if (st != CODA_OK) return st;
   layer_norm_bwd_finalize<<<(2 * c + 255) / 256, 256, 0, s>>>(nblk, c, partial, dgamma, dbeta);
   return launch_status();
+}
+
+int coda_layer_norm_bwd(long long rows, int c, const float *dy, const float *x, const float *gamma,
+                        const float *mean, const float *rstd, float *dx, float *dgamma,
+                        float *dbeta, float *partial, void *stream) {
+  return coda_layer_norm_bwd_ex(rows, c, dy, 0, 0, 0, nullptr, nullptr, x, gamma, mean, rstd, dx, dgamma, dbeta,
+                                partial, stream);
 }
 
 int coda_softmax_rows(long long rows, int c, int log_softmax, const float *x, float *y, void *stream) {

@@ -288,6 +288,96 @@ adamw_kernel(int nchunks, const coda_opt_chunk *__restrict__ chunks, float *__re
   }
 }
 
+// ------------------------------------------------------------------ n-ary gradient sum
+// out = src[0] + src[1] + ... + src[count - 1]: the fan-in of a tensor that several branches consumed (the six
+// prediction heads on the decoder output, the sixteen uses of the query embedding) as ONE pass that reads each
+// contribution once, instead of count - 1 `a + b` kernels that re-read and re-write the running sum.
+constexpr int SUM_MAX = 16;
+struct SumSrcs {
+  const float *p[SUM_MAX];
+};
+__global__ void __launch_bounds__(THREADS)
+sum_n_kernel(long long n, int count, const SumSrcs srcs, float *__restrict__ out) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < n4; i += (long long)gridDim.x * THREADS) {
+    float4 a = __ldg(reinterpret_cast<const float4 *>(srcs.p[0]) + i);
+    for (int j = 1; j < count; ++j) {
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(srcs.p[j]) + i);
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    reinterpret_cast<float4 *>(out)[i] = a;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    float a = srcs.p[0][i];
+    for (int j = 1; j < count; ++j) a += srcs.p[j][i];
+    out[i] = a;
+  }
+}
+
+// ------------------------------------------------------------------ masked L1 (cross-modal alignment loss)
+// out[l] = sum_{r, d} | pred[l][r][d] * w[r] - target[r][d] * w[r] |   (criterion.py:924-943: the products are formed
+// separately, as the reference does, so the value rounds the same way).  Two-stage deterministic sum.
+constexpr int L1_BLOCKS = 128;   // per layer
+__global__ void __launch_bounds__(THREADS)
+masked_l1_fwd_kernel(long long rows, int d, const float *__restrict__ pred, const float *__restrict__ target,
+                     const float *__restrict__ w, float *__restrict__ partial) {
+  const int layer = blockIdx.y;
+  const int d4 = d >> 2;
+  const long long n4 = rows * d4;
+  const float4 *p4 = reinterpret_cast<const float4 *>(pred) + (long long)layer * n4;
+  const float4 *t4 = reinterpret_cast<const float4 *>(target);
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < n4; i += (long long)gridDim.x * THREADS) {
+    const float wr = __ldg(w + i / d4);
+    const float4 a = __ldg(p4 + i), b = __ldg(t4 + i);
+    acc += (fabsf(a.x * wr - b.x * wr) + fabsf(a.y * wr - b.y * wr)) +
+           (fabsf(a.z * wr - b.z * wr) + fabsf(a.w * wr - b.w * wr));
+  }
+  __shared__ float red[THREADS / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < THREADS / 32; ++k) t += red[k];
+    partial[(long long)layer * gridDim.x + blockIdx.x] = t;
+  }
+}
+__global__ void masked_l1_finalize_kernel(int nblocks, const float *__restrict__ partial, float *__restrict__ out) {
+  double a = 0.0;
+  for (int k = threadIdx.x; k < nblocks; k += 32) a += (double)partial[(long long)blockIdx.x * nblocks + k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (threadIdx.x == 0) out[blockIdx.x] = (float)a;
+}
+// dpred[l][r][d] = g[l] * sgn(pred * w - target * w) * w[r]
+__global__ void __launch_bounds__(THREADS)
+masked_l1_bwd_kernel(long long rows, int d, const float *__restrict__ pred, const float *__restrict__ target,
+                     const float *__restrict__ w, const float *__restrict__ g, float *__restrict__ dpred) {
+  const int layer = blockIdx.y;
+  const int d4 = d >> 2;
+  const long long n4 = rows * d4;
+  const float4 *p4 = reinterpret_cast<const float4 *>(pred) + (long long)layer * n4;
+  const float4 *t4 = reinterpret_cast<const float4 *>(target);
+  float4 *o4 = reinterpret_cast<float4 *>(dpred) + (long long)layer * n4;
+  const float gl = __ldg(g + layer);
+  auto sgn = [](float v) { return (float)((v > 0.f) - (v < 0.f)); };
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < n4; i += (long long)gridDim.x * THREADS) {
+    const float wr = __ldg(w + i / d4);
+    const float4 a = __ldg(p4 + i), b = __ldg(t4 + i);
+    const float gw = gl * wr;
+    float4 o;
+    o.x = sgn(a.x * wr - b.x * wr) * gw;
+    o.y = sgn(a.y * wr - b.y * wr) * gw;
+    o.z = sgn(a.z * wr - b.z * wr) * gw;
+    o.w = sgn(a.w * wr - b.w * wr) * gw;
+    o4[i] = o;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -365,6 +455,45 @@ int coda_adamw_update(int nchunks, const coda_opt_chunk *chunks, float *param, c
   const int grid = nchunks < NUM_SMS * 8 ? nchunks : NUM_SMS * 8;
   adamw_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(nchunks, chunks, param, grad, exp_avg, exp_avg_sq, lr_dev,
                                                           grad_scale, beta1, beta2, eps, state);
+  return coda::launch_status();
+}
+
+int coda_sum_n(long long n, int count, const float *const *srcs, float *out, void *stream) {
+  if (n < 0 || count < 1 || count > SUM_MAX || !srcs) return CODA_EINVAL;
+  if (n == 0) return CODA_OK;
+  if (!out || ((uintptr_t)out & 15)) return CODA_EINVAL;
+  SumSrcs a;
+  for (int j = 0; j < SUM_MAX; ++j) {
+    a.p[j] = srcs[j < count ? j : 0];
+    if (!a.p[j] || ((uintptr_t)a.p[j] & 15)) return CODA_EINVAL;
+  }
+  sum_n_kernel<<<stream_grid(n / 4 + 1), THREADS, 0, (cudaStream_t)stream>>>(n, count, a, out);
+  return coda::launch_status();
+}
+
+long long coda_masked_l1_scratch_floats(int layers) { return (long long)(layers > 0 ? layers : 0) * L1_BLOCKS; }
+
+int coda_masked_l1_fwd(int layers, long long rows, int d, const float *pred, const float *target, const float *w,
+                       float *out, float *scratch, void *stream) {
+  if (layers < 0 || rows < 0 || d <= 0 || (d & 3)) return CODA_EINVAL;
+  if (layers == 0) return CODA_OK;
+  if (!pred || !target || !w || !out || !scratch || (((uintptr_t)pred | (uintptr_t)target) & 15)) return CODA_EINVAL;
+  cudaStream_t s = (cudaStream_t)stream;
+  masked_l1_fwd_kernel<<<dim3(L1_BLOCKS, layers), THREADS, 0, s>>>(rows, d, pred, target, w, scratch);
+  int st = coda::launch_status();
+  if (st != CODA_OK) return st;
+  masked_l1_finalize_kernel<<<layers, 32, 0, s>>>(L1_BLOCKS, scratch, out);
+  return coda::launch_status();
+}
+
+int coda_masked_l1_bwd(int layers, long long rows, int d, const float *pred, const float *target, const float *w,
+                       const float *g, float *dpred, void *stream) {
+  if (layers < 0 || rows < 0 || d <= 0 || (d & 3)) return CODA_EINVAL;
+  if (layers == 0 || rows == 0) return CODA_OK;
+  if (!pred || !target || !w || !g || !dpred || (((uintptr_t)pred | (uintptr_t)target | (uintptr_t)dpred) & 15))
+    return CODA_EINVAL;
+  masked_l1_bwd_kernel<<<dim3(L1_BLOCKS, layers), THREADS, 0, (cudaStream_t)stream>>>(rows, d, pred, target, w, g,
+                                                                                      dpred);
   return coda::launch_status();
 }
 

@@ -284,9 +284,11 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
         # (layer, batch, query) x channel the six heads share ONE packed GEMM operand and their outputs
         # land directly in (num_layers, batch, nqueries, out) order
         rows = box_features.permute(0, 2, 1, 3).reshape(num_layers * batch * num_queries, channel)
+        # six heads read the same rows: their six input gradients meet in one n-ary sum (ops.fanout)
+        taps = iter(ops.fanout(rows, 6))
 
         def head(name):
-            return self.mlp_heads[name].forward_rows(rows).view(num_layers, batch, num_queries, -1)
+            return self.mlp_heads[name].forward_rows(next(taps)).view(num_layers, batch, num_queries, -1)
 
         cls_logits = head("sem_cls_head")
         text_correlation_embedding = head("text_correlation_head")
@@ -593,7 +595,7 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
         query_xyz, query_embed = self.get_query_embeddings(enc_xyz, point_cloud_dims)
         enc_pos = self.pos_embedding(enc_xyz, input_range=point_cloud_dims).permute(2, 0, 1)
         query_embed = query_embed.permute(2, 0, 1)
-        tgt = torch.zeros_like(query_embed)
+        tgt = torch.zeros_like(query_embed, memory_format=torch.contiguous_format)
         box_features = self.decoder(tgt, enc_features, query_pos=query_embed, pos=enc_pos)[0]
         box_predictions = self.get_box_predictions(query_xyz, point_cloud_dims, box_features, point_clouds, inputs)
         out = box_predictions["outputs"]

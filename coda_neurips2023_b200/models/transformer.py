@@ -205,15 +205,13 @@ class TransformerEncoderLayer(nn.Module):
 
     def forward_pre(self, src, src_mask=None, src_key_padding_mask=None, pos=None, return_attn_weights=False):
         # reference transformer.py:461-479
-        src2 = self.norm1(src)
-        if pos is None:
-            attn = self.self_attn(src2, src2, src2, attn_mask=src_mask, key_padding_mask=src_key_padding_mask)[0]
-        else:
-            qk = src2 + pos
-            attn = self.self_attn(qk, qk, src2, attn_mask=src_mask, key_padding_mask=src_key_padding_mask)[0]
+        # norm -> (residual operand, norm(src), norm(src) + pos) as one node: the joins of the residual branch and of
+        # the `+ pos` branch happen inside the LayerNorm kernels (ops.layer_norm_branch)
+        src, src2, qk = ops.layer_norm_branch(src, self.norm1, pos)
+        attn = self.self_attn(qk, qk, src2, attn_mask=src_mask, key_padding_mask=src_key_padding_mask)[0]
         src = ops.dropout_add(attn, src, self.dropout1.p, self.training)
         if self.use_ffn:
-            src2 = self.norm2(src)
+            src, src2, _ = ops.layer_norm_branch(src, self.norm2)
             src2 = self.linear2(ops.dropout(_ffn_hidden(self, src2), self.dropout.p, self.training))
             src = ops.dropout_add(src2, src, self.dropout2.p, self.training)
         if return_attn_weights:
@@ -278,13 +276,31 @@ class TransformerDecoder(nn.Module):
             kv = ops.kv_bank(mem_key, memory, cross)
         output = tgt
         intermediate = []
+        # every layer adds the query embedding twice (self- and cross-attention): its 2 x num_layers gradient
+        # contributions meet in one n-ary sum (ops.fanout) instead of a chain of binary adds
+        if query_pos is not None and not query_pos.is_contiguous():
+            query_pos = query_pos.contiguous()      # once, not once per use inside the fused norm kernels
+        qp = None if query_pos is None else ops.fanout(query_pos, 2 * len(self.layers))
+        stacked = self.return_intermediate and self.norm is not None
+        outputs = []
         for idx, layer in enumerate(self.layers):
             output, _ = layer(output, memory, tgt_mask=tgt_mask, memory_mask=memory_mask,
                               tgt_key_padding_mask=tgt_key_padding_mask,
-                              memory_key_padding_mask=memory_key_padding_mask, pos=pos, query_pos=query_pos,
-                              memory_key=mem_key, kv_bank=None if kv is None else (kv[0], kv[1], idx))
-            if self.return_intermediate:
+                              memory_key_padding_mask=memory_key_padding_mask, pos=pos,
+                              query_pos=None if qp is None else qp[2 * idx],
+                              memory_key=mem_key, kv_bank=None if kv is None else (kv[0], kv[1], idx),
+                              query_pos_cross=None if qp is None else qp[2 * idx + 1])
+            if stacked:
+                outputs.append(output)
+            elif self.return_intermediate:
                 intermediate.append(self.norm(output))
+        if stacked and ops.norm_stack_applicable(self.norm, outputs):
+            # (layers, batch, query, channel) buffer, returned as the reference's (layers, query, batch, channel)
+            # view of it: the prediction heads' permute + reshape (models/model_3detr.py get_box_predictions) is free
+            return ops.norm_stack(self.norm, outputs).permute(0, 2, 1, 3), []
+        if stacked:
+            intermediate = [self.norm(o) for o in outputs]
+            return torch.stack(intermediate), []
         if self.norm is not None:
             output = self.norm(output)
             if self.return_intermediate:
@@ -333,32 +349,35 @@ class TransformerDecoderLayer(nn.Module):
 
     def forward_pre(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
                     memory_key_padding_mask=None, pos=None, query_pos=None, return_attn_weights=False,
-                    memory_key=None, kv_bank=None):
+                    memory_key=None, kv_bank=None, query_pos_cross=None):
         # reference transformer.py:556-580
         if memory_key is None:
             memory_key = self.with_pos_embed(memory, pos)
-        tgt2 = self.norm1(tgt)
-        qk = self.with_pos_embed(tgt2, query_pos)
+        if query_pos_cross is None:
+            query_pos_cross = query_pos
+        # each norm is one node with the residual by-pass and the `+ query_pos` operand (ops.layer_norm_branch)
+        tgt, tgt2, qk = ops.layer_norm_branch(tgt, self.norm1, query_pos)
         tgt2 = self.self_attn(qk, qk, tgt2, attn_mask=tgt_mask, key_padding_mask=tgt_key_padding_mask)[0]
         tgt = ops.dropout_add(tgt2, tgt, self.dropout1.p, self.training)
-        tgt2 = self.norm2(tgt)
-        tgt2 = self._cross(self.with_pos_embed(tgt2, query_pos), memory_key, memory, memory_mask,
-                           memory_key_padding_mask, kv_bank)
+        tgt, _, q = ops.layer_norm_branch(tgt, self.norm2, query_pos_cross, want_y=False)
+        tgt2 = self._cross(q, memory_key, memory, memory_mask, memory_key_padding_mask, kv_bank)
         tgt = ops.dropout_add(tgt2, tgt, self.dropout2.p, self.training)
-        tgt2 = self.norm3(tgt)
+        tgt, tgt2, _ = ops.layer_norm_branch(tgt, self.norm3)
         tgt2 = self.linear2(ops.dropout(_ffn_hidden(self, tgt2), self.dropout.p, self.training))
         tgt = ops.dropout_add(tgt2, tgt, self.dropout3.p, self.training)
         return tgt, None
 
     def forward_post(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
                      memory_key_padding_mask=None, pos=None, query_pos=None, return_attn_weights=False,
-                     memory_key=None, kv_bank=None):
+                     memory_key=None, kv_bank=None, query_pos_cross=None):
         if memory_key is None:
             memory_key = self.with_pos_embed(memory, pos)
+        if query_pos_cross is None:
+            query_pos_cross = query_pos
         qk = self.with_pos_embed(tgt, query_pos)
         tgt2 = self.self_attn(qk, qk, tgt, attn_mask=tgt_mask, key_padding_mask=tgt_key_padding_mask)[0]
         tgt = self.norm1(ops.dropout_add(tgt2, tgt, self.dropout1.p, self.training))
-        tgt2 = self._cross(self.with_pos_embed(tgt, query_pos), memory_key, memory, memory_mask,
+        tgt2 = self._cross(self.with_pos_embed(tgt, query_pos_cross), memory_key, memory, memory_mask,
                            memory_key_padding_mask, kv_bank)
         tgt = self.norm2(ops.dropout_add(tgt2, tgt, self.dropout2.p, self.training))
         tgt2 = self.linear2(ops.dropout(_ffn_hidden(self, tgt), self.dropout.p, self.training))
@@ -367,7 +386,7 @@ class TransformerDecoderLayer(nn.Module):
 
     def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
                 memory_key_padding_mask=None, pos=None, query_pos=None, return_attn_weights=False,
-                memory_key=None, kv_bank=None):
+                memory_key=None, kv_bank=None, query_pos_cross=None):
         fn = self.forward_pre if self.normalize_before else self.forward_post
         return fn(tgt, memory, tgt_mask, memory_mask, tgt_key_padding_mask, memory_key_padding_mask, pos,
-                  query_pos, return_attn_weights, memory_key, kv_bank)
+                  query_pos, return_attn_weights, memory_key, kv_bank, query_pos_cross)

@@ -183,6 +183,243 @@ class LayerNorm(torch.nn.LayerNorm):
         return layer_norm(x, self.weight, self.bias, self.eps)
 
 
+def _ln_backward(rows, c, dy, dmap, dy2, add, xc, weight, bias, mean, rstd, dx, dgamma=None, dbeta=None):
+    """one coda_layer_norm_bwd_ex launch (+ its finalize); dgamma / dbeta: destination or None -> (sink | new).
+    Returns (dgamma, dbeta) as they go back to autograd (None when written into the flat gradient buffer)."""
+    own = dgamma is not None
+    sg = sb = None
+    if not own:
+        sg, sb = _sink(weight), _sink(bias)
+        if sg is None or sb is None:
+            sg = sb = None
+        dgamma = torch.empty_like(weight) if sg is None else sg
+        dbeta = torch.empty_like(weight) if sb is None else sb
+    nscratch = lib().coda_layer_norm_bwd_scratch(_ll(rows), _i(c))
+    partial = torch.empty(max(int(nscratch), 1), dtype=torch.float32, device=xc.device)
+    inner, so, si = dmap
+    with torch.cuda.device(xc.device):
+        st = lib().coda_layer_norm_bwd_ex(_ll(rows), _i(c), ptr(dy), _i(inner), _ll(so), _ll(si), ptr(dy2), ptr(add),
+                                          ptr(xc), ptr(weight), ptr(mean), ptr(rstd), ptr(dx), ptr(dgamma), ptr(dbeta),
+                                          ptr(partial), stream_of(xc))
+    check(st, "layer_norm_bwd_ex")
+    if sg is not None:
+        return _sunk(sg), _sunk(sb)
+    return dgamma, dbeta
+
+
+class _LayerNormBranch(torch.autograd.Function):
+    """The head of a pre-norm transformer sub-block as ONE autograd node:
+
+        x  ->  (x, norm(x), norm(x) + pos)
+
+    `x` passes through so that the gradient of the residual branch arrives at this node and is added to the norm's
+    input gradient inside the backward kernel; `norm(x) + pos` (the q = k operand, reference
+    models/transformer.py:556-580 `with_pos_embed`) is a second store of the forward kernel and a second load of the
+    backward one.  Autograd's own wiring runs an `a + b` kernel for each of those joins."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, pos, want_y):
+        _need_cuda(x, "layer_norm_branch")
+        ctx.set_materialize_grads(False)
+        xc = _f32c(x)
+        c = xc.shape[-1]
+        rows = xc.numel() // c
+        y = torch.empty_like(xc) if want_y else None
+        pc = ypos = None
+        if pos is not None:
+            assert pos.shape == x.shape, "pos must have the shape of x"
+            pc = _f32c(pos)
+            ypos = torch.empty_like(xc)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            st = lib().coda_layer_norm_fwd_ex(_ll(rows), _i(c), _f(eps), ptr(xc), ptr(weight), ptr(bias), ptr(y), _i(0),
+                                              _ll(0), _ll(0), ptr(pc), ptr(ypos), ptr(mean), ptr(rstd), stream_of(x))
+        check(st, "layer_norm_fwd_ex")
+        ctx.save_for_backward(xc, weight, bias, mean, rstd)
+        ctx.pos_grad = pos is not None and pos.requires_grad
+        # the residual operand: `x` itself, or its contiguous copy when one had to be made (the consumer would
+        # otherwise copy it again)
+        return (x if xc.data_ptr() == x.data_ptr() else xc), y, ypos
+
+    @staticmethod
+    def backward(ctx, g_id, g_y, g_ypos):
+        xc, weight, bias, mean, rstd = ctx.saved_tensors
+        c = xc.shape[-1]
+        rows = xc.numel() // c
+        ds = [_f32c(g) for g in (g_y, g_ypos) if g is not None]
+        if not ds:                                # the norm's outputs were not used: only the by-pass gradient
+            ds = [torch.zeros_like(xc)]
+        add = None if g_id is None else _f32c(g_id)
+        dx = torch.empty_like(xc)
+        dgamma, dbeta = _ln_backward(rows, c, ds[0], (0, 0, 0), ds[1] if len(ds) > 1 else None, add, xc, weight, bias,
+                                     mean, rstd, dx)
+        return dx, dgamma, dbeta, None, (g_ypos if ctx.pos_grad else None), None
+
+
+def layer_norm_branch(x: torch.Tensor, norm: torch.nn.Module, pos: torch.Tensor | None = None, want_y: bool = True):
+    """-> (x_resid, y, y_pos): x_resid is `x` (use it as the residual operand), y = norm(x) (None unless want_y),
+    y_pos = y + pos (y itself when pos is None).  Any other norm module takes the plain sequence of ops."""
+    if not (isinstance(norm, LayerNorm) and x.is_cuda and x.dtype == torch.float32
+            and norm.weight.shape[0] % 128 == 0 and norm.weight.shape[0] <= 1024
+            and (pos is None or (pos.shape == x.shape and pos.dtype == torch.float32))):
+        y = norm(x)
+        return x, (y if want_y else None), (y if pos is None else y + pos)
+    if pos is None:
+        x_id, y, _ = _LayerNormBranch.apply(x, norm.weight, norm.bias, float(norm.eps), None, True)
+        return x_id, y, y
+    return _LayerNormBranch.apply(x, norm.weight, norm.bias, float(norm.eps), pos, bool(want_y))
+
+
+class _NormStack(torch.autograd.Function):
+    """norm(x_l) of every decoder layer's output (reference models/transformer.py:122-137 `intermediate`), written
+    straight into ONE (layers, batch, query, channel) buffer -- the order the prediction heads read
+    (models/model_3detr.py:1634-1650 permutes the (layers, query, batch, channel) stack) -- so that neither the
+    torch.stack copy, nor the permuting copy, nor their strided gradient slices exist."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, eps, *xs):
+        nl = len(xs)
+        q, b, c = xs[0].shape
+        rows = q * b
+        dev = xs[0].device
+        xcs = [_f32c(x) for x in xs]
+        out = torch.empty((nl, b, q, c), dtype=torch.float32, device=dev)
+        mean = torch.empty((nl, rows), dtype=torch.float32, device=dev)
+        rstd = torch.empty((nl, rows), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            for l, xc in enumerate(xcs):
+                st = lib().coda_layer_norm_fwd_ex(_ll(rows), _i(c), _f(eps), ptr(xc), ptr(weight), ptr(bias), ptr(out[l]),
+                                                  _i(b), _ll(c), _ll(q * c), None, None, ptr(mean[l]), ptr(rstd[l]),
+                                                  stream_of(xc))
+                check(st, "layer_norm_fwd_ex")
+        ctx.save_for_backward(weight, bias, mean, rstd, *xcs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        weight, bias, mean, rstd = ctx.saved_tensors[:4]
+        xcs = ctx.saved_tensors[4:]
+        nl = len(xcs)
+        q, b, c = xcs[0].shape
+        rows = q * b
+        dc = _f32c(dout)
+        dev = dc.device
+        dgam = torch.empty((nl, c), dtype=torch.float32, device=dev)
+        dbet = torch.empty((nl, c), dtype=torch.float32, device=dev)
+        dxs = []
+        for l, xc in enumerate(xcs):
+            dx = torch.empty_like(xc)
+            _ln_backward(rows, c, dc[l], (b, c, q * c), None, None, xc, weight, bias, mean[l], rstd[l], dx,
+                         dgamma=dgam[l], dbeta=dbet[l])
+            dxs.append(dx)
+        sg, sb = _sink(weight), _sink(bias)
+        if sg is None or sb is None:
+            sg = sb = None
+        dgamma = sum_tensors([dgam[l] for l in range(nl)], out=sg)
+        dbeta = sum_tensors([dbet[l] for l in range(nl)], out=sb)
+        if sg is not None:
+            dgamma, dbeta = _sunk(sg), _sunk(sb)
+        return (dgamma, dbeta, None, *dxs)
+
+
+def norm_stack(norm: torch.nn.Module, xs) -> torch.Tensor:
+    """[(Q, B, C)] * layers -> (layers, B, Q, C) = norm of every entry; see _NormStack"""
+    return _NormStack.apply(norm.weight, norm.bias, float(norm.eps), *xs)
+
+
+def norm_stack_applicable(norm, xs) -> bool:
+    return (isinstance(norm, LayerNorm) and len(xs) > 0 and all(x.is_cuda and x.dtype == torch.float32 and x.dim() == 3
+                                                               and x.shape == xs[0].shape for x in xs)
+            and xs[0].shape[-1] % 128 == 0 and xs[0].shape[-1] <= 1024)
+
+
+# --------------------------------------------------------------------------- gradient fan-in
+_SUM_MAX = 16
+
+
+def sum_tensors(ts, out: torch.Tensor | None = None) -> torch.Tensor:
+    """sum of same-shape fp32 CUDA tensors in one pass per 16 operands (coda_sum_n); `out` may be one of them"""
+    ts = [_f32c(t) for t in ts]
+    if out is None:
+        out = torch.empty_like(ts[0])
+    assert out.is_contiguous() and all(t.shape == ts[0].shape for t in ts)
+    n = ts[0].numel()
+    with torch.cuda.device(out.device):
+        while True:
+            head, ts = ts[:_SUM_MAX], ts[_SUM_MAX:]
+            arr = (ctypes.c_void_p * len(head))(*[t.data_ptr() for t in head])
+            check(lib().coda_sum_n(_ll(n), _i(len(head)), arr, ptr(out), stream_of(out)), "sum_n")
+            if not ts:
+                return out
+            ts = [out] + ts
+
+
+class _FanOut(torch.autograd.Function):
+    """x -> n aliases of x whose gradients meet in ONE n-ary sum (autograd's accumulation: n - 1 binary adds, each
+    re-reading and re-writing the running sum)."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.set_materialize_grads(False)
+        return tuple(x.detach() for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        gs = [g for g in gs if g is not None]
+        if not gs:
+            return None, None
+        if len(gs) == 1:
+            return gs[0], None
+        return sum_tensors(gs), None
+
+
+def fanout(x: torch.Tensor, n: int):
+    """n handles on `x` for n consumers; use when a large activation feeds several branches"""
+    if n <= 1 or not (x.is_cuda and x.dtype == torch.float32 and x.requires_grad and torch.is_grad_enabled()):
+        return (x,) * max(n, 1)
+    return _FanOut.apply(x, n)
+
+
+# --------------------------------------------------------------------------- masked L1 (alignment loss)
+class _MaskedL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, w):
+        nl = pred.shape[0]
+        d = pred.shape[-1]
+        rows = pred[0].numel() // d
+        out = torch.empty(nl, dtype=torch.float32, device=pred.device)
+        scratch = torch.empty(nl * 128, dtype=torch.float32, device=pred.device)
+        with torch.cuda.device(pred.device):
+            check(lib().coda_masked_l1_fwd(_i(nl), _ll(rows), _i(d), ptr(pred), ptr(target), ptr(w), ptr(out),
+                                           ptr(scratch), stream_of(pred)), "masked_l1_fwd")
+        ctx.save_for_backward(pred, target, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target, w = ctx.saved_tensors
+        nl = pred.shape[0]
+        d = pred.shape[-1]
+        rows = pred[0].numel() // d
+        gc = _f32c(g)
+        dpred = torch.empty_like(pred)
+        with torch.cuda.device(pred.device):
+            check(lib().coda_masked_l1_bwd(_i(nl), _ll(rows), _i(d), ptr(pred), ptr(target), ptr(w), ptr(gc), ptr(dpred),
+                                           stream_of(pred)), "masked_l1_bwd")
+        return dpred, None, None
+
+
+def masked_l1(pred: torch.Tensor, target: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """(layers,) sums of |pred * w - target * w| with pred (layers, ..., d), target (..., d) broadcast over the layers and
+    w (..., 1) or (...) one weight per row (reference criterion.py:924-943); target and w carry no gradient."""
+    _need_cuda(pred, "masked_l1")
+    d = pred.shape[-1]
+    assert d % 4 == 0 and pred.shape[1:] == target.shape and w.numel() == target.numel() // d
+    assert not target.requires_grad and not w.requires_grad
+    return _MaskedL1.apply(_f32c(pred), _f32c(target), _f32c(w).reshape(-1))
+
+
 # --------------------------------------------------------------------------- dropout / residual
 _uint = ctypes.c_uint
 
@@ -876,12 +1113,36 @@ class _Linear(torch.autograd.Function):
         # gradients are held to a looser bar than the forward (5e-3 vs 1e-4): two planes suffice
         nsplit = min(ctx.nsplit, BACKWARD_NSPLIT)
         dy = dy.contiguous()
-        if ctx.relu:
-            dy = dy * (y > 0).to(dy.dtype)
         m, k = x.shape
         n = weight.shape[0]
         dx = dw = db = None
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        # ReLU backward: dZ = [y > 0] * dY.  Both consumers of dZ are GEMMs whose A prologue can evaluate it from
+        # (y, dY) while splitting the operand (the BatchNorm-backward prologue with scale 1, everything else 0), so
+        # the masked gradient is never written: no compare / cast / multiply kernels in front of the GEMMs.
+        pro = None
+        if ctx.relu:
+            if (a32_ok(dy) and a32_ok(y) and tn32_ok(dy) and tn32_ok(x) and k % 4 == 0 and nsplit == 2
+                    and ctx.needs_input_grad[1]):
+                one, zero = _unit_vectors(n, dy.device)
+                pro = dict(scale=one, shift=zero, alpha=zero, beta=zero)
+            else:
+                dy = dy * (y > 0).to(dy.dtype)
+        if pro is not None:
+            if ctx.needs_input_grad[0]:
+                dx = gemm_a32(y, _packed_weight(weight, False, ctx.nsplit), k, mode=A32_BN_BWD, a2=dy, b_mn=True,
+                              nsplit=nsplit, **pro)
+            sw, sb = _sink(weight), None
+            if want_db:
+                sb = _sink(bias)
+                db = torch.empty(n, dtype=torch.float32, device=dy.device) if sb is None else sb
+            dw = gemm_tn32(y, x, a_mode=A32_BN_BWD, a2=dy, a_scale=one, a_shift=zero, a_alpha=zero, a_beta=zero,
+                           out=sw, colsum_out=db)
+            if sw is not None:
+                dw = _sunk(sw)
+            if sb is not None:
+                db = _sunk(sb)
+            return dx, dw, db, None, None
         if ctx.needs_input_grad[0]:
             if a32_ok(dy) and k % 4 == 0:
                 # dX (m, k) = dY (m, n) @ W (n, k): contraction over the ROWS of the forward weight planes
@@ -912,6 +1173,20 @@ class _Linear(torch.autograd.Function):
             if sb is not None:
                 db = _sunk(sb)
         return dx, dw, db, None, None
+
+
+_UNIT: dict = {}
+
+
+def _unit_vectors(n: int, device):
+    """(ones, zeros) of n floats rounded up to 128: the per-column coefficient vectors that turn the BatchNorm-backward prologue
+    into a plain ReLU mask"""
+    key = ((n + 127) // 128 * 128, device)
+    hit = _UNIT.get(key)
+    if hit is None:
+        hit = _UNIT[key] = (torch.ones(key[0], dtype=torch.float32, device=device),
+                            torch.zeros(key[0], dtype=torch.float32, device=device))
+    return hit
 
 
 _BIAS32: dict = {}

@@ -26,6 +26,19 @@ int coda_layer_norm_fwd(long long rows, int c, float eps, const float *x,
                         const float *gamma, const float *beta, float *y,
                         float *mean, float *rstd, void *stream);
 /*
+ * The same with the transformer layer's neighbours folded in (models/transformer.py:556-580: `tgt2 = self.norm1(tgt);
+ * q = k = self.with_pos_embed(tgt2, query_pos)`; models/transformer.py:97-143: the decoder's `self.norm(output)` of
+ * every layer stacked, which models/model_3detr.py:1634-1650 then permutes to (layer, batch, query)):
+ *   y      may be NULL; row r of y is written at  r * c  floats when y_inner == 0, else at
+ *          (r / y_inner) * y_so + (r % y_inner) * y_si  (multiples of 4) -- a row permutation / a slice of a larger
+ *          buffer without a copy
+ *   y_pos  (rows, c) = y + pos  when pos != NULL (both or neither)
+ */
+int coda_layer_norm_fwd_ex(long long rows, int c, float eps, const float *x,
+                           const float *gamma, const float *beta, float *y, int y_inner,
+                           long long y_so, long long y_si, const float *pos, float *y_pos,
+                           float *mean, float *rstd, void *stream);
+/*
  * Forward-only variant for fp16 activations: x, y are IEEE half (rows, c); gamma,
  * beta fp32; statistics in fp32 and one rounding to half at the end.
  *   replaces the fp32-upcasting LayerNorm of the CLIP towers
@@ -44,6 +57,18 @@ int coda_layer_norm_bwd(long long rows, int c, const float *dy, const float *x,
                         const float *gamma, const float *mean, const float *rstd,
                         float *dx, float *dgamma, float *dbeta, float *partial,
                         void *stream);
+/*
+ * Backward of coda_layer_norm_fwd_ex and of the residual connection around the norm, in one pass:
+ *   d  = dy (row-mapped like y above) + dy2 (optional (rows, c): the gradient that arrived through y_pos)
+ *   dx = LayerNormBackward(d) + add   (add optional (rows, c): the gradient of `tgt` through the branch that
+ *        by-passes the norm -- autograd would otherwise run a separate `grad_a + grad_b` kernel per norm)
+ *   dgamma / dbeta from d.  dx may alias dy, dy2 or add.
+ */
+int coda_layer_norm_bwd_ex(long long rows, int c, const float *dy, int dy_inner, long long dy_so,
+                           long long dy_si, const float *dy2, const float *add, const float *x,
+                           const float *gamma, const float *mean, const float *rstd,
+                           float *dx, float *dgamma, float *dbeta, float *partial,
+                           void *stream);
 
 /*
  * Row softmax / log-softmax over the last dimension (any c >= 1), one warp per row.

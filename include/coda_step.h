@@ -53,6 +53,29 @@ int coda_bn_act_rows_bwd(long long rows, int c, const float *y, const float *dou
                          void *stream);
 
 /*
+ * out[i] = srcs[0][i] + ... + srcs[count - 1][i], 1 <= count <= 16; `srcs` is a HOST array of device pointers
+ * (16-byte aligned).  The gradient fan-in of a tensor consumed by several branches (the six prediction heads of
+ * models/model_3detr.py:1634-1660 on the decoder output, the 2 x dec_nlayers uses of the query embedding in
+ * models/transformer.py:556-580) in one pass -- autograd's own accumulation runs count - 1 binary adds.
+ * out may alias any of the sources.
+ */
+int coda_sum_n(long long n, int count, const float *const *srcs, float *out, void *stream);
+
+/*
+ * Masked L1 between the heads' 512-d embedding and the CLIP embedding of the boxes' image crops
+ * (criterion.py:924-943 loss_predicted_region_embed_l1):
+ *   out[l] = sum_{r, k} | pred[l][r][k] * w[r] - target[r][k] * w[r] |,  pred (layers, rows, d), target (rows, d),
+ *   w (rows), d % 4 == 0; the target is broadcast over the layers, not repeated.  Deterministic two-stage sum;
+ *   scratch: coda_masked_l1_scratch_floats(layers) floats.
+ *   backward: dpred[l][r][k] = g[l] * sgn(pred * w - target * w) * w[r]
+ */
+long long coda_masked_l1_scratch_floats(int layers);
+int coda_masked_l1_fwd(int layers, long long rows, int d, const float *pred, const float *target, const float *w,
+                       float *out, float *scratch, void *stream);
+int coda_masked_l1_bwd(int layers, long long rows, int d, const float *pred, const float *target, const float *w,
+                       const float *g, float *dpred, void *stream);
+
+/*
  * Global-norm gradient clip + AdamW over ONE flat fp32 parameter buffer.
  *
  * coda_grad_norm: state[1] = ||grad * grad_scale||_2 over the `n` elements (deterministic two-stage sum, fp64

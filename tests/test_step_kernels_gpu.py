@@ -210,3 +210,148 @@ def test_train_step_prepare_and_capture_leave_no_trace():
             assert torch.allclose(p, wg[n], rtol=1e-4, atol=1e-6), n
             changed += int(not torch.equal(p, w0[n]))
     assert changed > 100
+
+
+# ------------------------------------------------------------------ fused autograd joins (round 2)
+def _ln_ref(x, w, b, eps=1e-5):
+    return torch.nn.functional.layer_norm(x, (x.shape[-1],), w, b, eps)
+
+
+@pytest.mark.parametrize("q,b,c,with_pos,want_y", [(256, 8, 512, True, True), (256, 8, 512, True, False),
+                                                   (100, 3, 256, False, True), (2048, 8, 256, False, True)])
+def test_layer_norm_branch_matches_the_unfused_graph(q, b, c, with_pos, want_y):
+    """(x, norm(x), norm(x) + pos) as one node == x / LayerNorm / add as three, values and every gradient (the
+    residual by-pass gradient and the `+ pos` gradient are added inside the backward kernel)"""
+    from coda_neurips2023_b200 import ops
+
+    torch.manual_seed(q + c)
+    norm = ops.LayerNorm(c).cuda()
+    with torch.no_grad():
+        norm.weight.normal_(1.0, 0.2)
+        norm.bias.normal_(0.0, 0.2)
+    x = torch.randn(q, b, c, device="cuda", requires_grad=True)
+    pos = torch.randn(q, b, c, device="cuda", requires_grad=True) if with_pos else None
+    x_id, y, yp = ops.layer_norm_branch(x, norm, pos, want_y=want_y)
+    xr = x.detach().double().requires_grad_(True)
+    pr = pos.detach().double().requires_grad_(True) if with_pos else None
+    wr, br = norm.weight.detach().double().requires_grad_(True), norm.bias.detach().double().requires_grad_(True)
+    yr = _ln_ref(xr, wr, br)
+    ypr = yr + pr if with_pos else yr
+    assert x_id.data_ptr() == x.data_ptr()
+    # a strided input comes back as its contiguous copy (same values), not as a second strided operand
+    xs = torch.randn(b, c, q, device="cuda").permute(2, 0, 1)
+    xs_id, ys, _ = ops.layer_norm_branch(xs, norm)
+    assert xs_id.is_contiguous() and torch.equal(xs_id, xs)
+    torch.testing.assert_close(ys, _ln_ref(xs, norm.weight, norm.bias), rtol=1e-5, atol=1e-5)
+    if want_y:
+        torch.testing.assert_close(y.double(), yr, rtol=1e-5, atol=1e-5)
+    else:
+        assert y is None
+    torch.testing.assert_close(yp.double(), ypr, rtol=1e-5, atol=1e-5)
+    g1, g2, g3 = (torch.randn(q, b, c, device="cuda") for _ in range(3))
+    loss = (x_id * g1).sum() + (yp * g3).sum() + ((y * g2).sum() if want_y and with_pos else 0.0)
+    ref = (xr * g1.double()).sum() + (ypr * g3.double()).sum() + ((yr * g2.double()).sum() if want_y and with_pos else 0.0)
+    ins = [x, norm.weight, norm.bias] + ([pos] if with_pos else [])
+    rins = [xr, wr, br] + ([pr] if with_pos else [])
+    got = torch.autograd.grad(loss, ins)
+    exp = torch.autograd.grad(ref, rins)
+    for gg, ee in zip(got, exp):
+        assert ((gg.double() - ee).abs().max() / ee.abs().max()).item() < 2e-5
+
+
+def test_norm_stack_writes_the_heads_layout_and_its_backward():
+    """norm of every decoder layer's output straight into (layers, batch, query, channel): equals
+    torch.stack([norm(x_l)]).permute(0, 2, 1, 3), gradients included (gamma / beta summed over the layers)"""
+    from coda_neurips2023_b200 import ops
+
+    torch.manual_seed(9)
+    nl, q, b, c = 4, 96, 3, 256
+    norm = ops.LayerNorm(c).cuda()
+    with torch.no_grad():
+        norm.weight.normal_(1.0, 0.2)
+        norm.bias.normal_(0.0, 0.2)
+    xs = [torch.randn(q, b, c, device="cuda", requires_grad=True) for _ in range(nl)]
+    assert ops.norm_stack_applicable(norm, xs)
+    out = ops.norm_stack(norm, xs)
+    assert out.shape == (nl, b, q, c) and out.is_contiguous()
+    xr = [x.detach().double().requires_grad_(True) for x in xs]
+    wr, br = norm.weight.detach().double().requires_grad_(True), norm.bias.detach().double().requires_grad_(True)
+    ref = torch.stack([_ln_ref(x, wr, br) for x in xr]).permute(0, 2, 1, 3)
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
+    g = torch.randn(nl, b, q, c, device="cuda")
+    got = torch.autograd.grad(out, [norm.weight, norm.bias, *xs], g)
+    exp = torch.autograd.grad(ref, [wr, br, *xr], g.double())
+    for gg, ee in zip(got, exp):
+        assert ((gg.double() - ee).abs().max() / ee.abs().max()).item() < 2e-5
+
+
+@pytest.mark.parametrize("n,count", [(8 * 256 * 512, 6), (1027, 3), (4096, 16), (4100, 21), (12, 1)])
+def test_sum_tensors_and_fanout(n, count):
+    from coda_neurips2023_b200 import ops
+
+    torch.manual_seed(n)
+    ts = [torch.randn(n, device="cuda") for _ in range(count)]
+    ref = torch.stack([t.double() for t in ts]).sum(0)
+    got = ops.sum_tensors(ts)
+    assert ((got.double() - ref).abs().max() / ref.abs().max()).item() < 2e-6
+    x = torch.randn(n, device="cuda", requires_grad=True)
+    taps = ops.fanout(x, count)
+    assert len(taps) == count and all(t.data_ptr() == x.data_ptr() for t in taps)
+    loss = sum((t * w).sum() for t, w in zip(taps, ts))
+    (gx,) = torch.autograd.grad(loss, x)
+    assert ((gx.double() - ref).abs().max() / ref.abs().max()).item() < 2e-6
+    # unused taps contribute nothing
+    if count > 2:
+        taps = ops.fanout(x, count)
+        (gx,) = torch.autograd.grad((taps[0] * ts[0]).sum() + (taps[2] * ts[2]).sum(), x)
+        torch.testing.assert_close(gx, ts[0] + ts[2])
+
+
+@pytest.mark.parametrize("nl,b,q,d", [(7, 8, 256, 512), (1, 2, 50, 64)])
+def test_masked_l1_matches_the_reference_expression(nl, b, q, d):
+    """reference criterion.py:924-943: (pred * w - target * w).abs().sum over everything but the layer"""
+    from coda_neurips2023_b200 import ops
+
+    torch.manual_seed(nl)
+    pred = torch.randn(nl, b, q, d, device="cuda", requires_grad=True)
+    target = torch.randn(b, q, d, device="cuda")
+    w = (torch.rand(b, q, 1, device="cuda") > 0.6).float()
+    with torch.no_grad():
+        pred[0, 0, 0, :8] = target[0, 0, :8]          # exact zeros: sgn(0) = 0
+    out = ops.masked_l1(pred, target, w)
+    pr = pred.detach().double().requires_grad_(True)
+    ref = (pr * w.double() - target.double() * w.double()).abs().sum(dim=(1, 2, 3))
+    assert ((out.double() - ref).abs() / ref).max().item() < 1e-6
+    g = torch.rand(nl, device="cuda") + 0.5
+    (got,) = torch.autograd.grad(out, pred, g)
+    (exp,) = torch.autograd.grad(ref, pr, g.double())
+    torch.testing.assert_close(got.double(), exp, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("m,k,n", [(16384, 256, 128), (2048, 512, 256), (3000, 256, 512), (2048, 512, 512)])
+def test_linear_relu_backward_masks_inside_the_gemms(m, k, n):
+    """y = relu(x W^T + b): the backward evaluates [y > 0] * dY in the A prologue of both gradient GEMMs -- same
+    values as masking first (the fallback for shapes the prologue does not take)"""
+    from coda_neurips2023_b200 import ops
+
+    torch.manual_seed(m + n)
+    x = torch.randn(m, k, device="cuda", requires_grad=True)
+    w = (torch.randn(n, k, device="cuda") * 0.05).requires_grad_(True)
+    b = torch.randn(n, device="cuda", requires_grad=True)
+    y = ops.linear(x, w, b, relu=True)
+    g = torch.randn_like(y)
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), g)
+    # the same backward on a pre-masked gradient through the plain (relu = False) node
+    y0 = ops.linear(x, w, b, relu=False)
+    gm = g * (y0.detach() > 0).float()
+    rx, rw, rb = torch.autograd.grad(y0, (x, w, b), gm)
+    # same operand values through the same tensor-core sequence; the split-K partition of the weight gradient may
+    # differ between the two prologues (fp32 re-association): compare on the scale of the result
+    for got, exp in ((gx, rx), (gw, rw)):
+        assert ((got - exp).abs().max() / exp.abs().max()).item() < 2e-6
+    torch.testing.assert_close(gb, rb, rtol=1e-5, atol=1e-4)
+    # and against fp64 with the mask the forward produced (an fp64 forward flips the mask where y is within rounding
+    # of zero, which is not an error of the backward)
+    gd = gm.double()
+    for got, exp in ((gx, gd @ w.detach().double()), (gw, gd.t() @ x.detach().double()), (gb, gd.sum(0))):
+        assert ((got.double() - exp).abs().max() / exp.abs().max()).item() < 3e-5
