@@ -127,7 +127,14 @@ class VisionTransformer(nn.Module):
     def forward(self, x: torch.Tensor, im_name=None, max_w=None, if_pool=True, if_early_feat=False):
         """(N, 3, R, R) -> (cls embedding (N, output_dim), all tokens (N, grid^2 + 1, output_dim))"""
         ps = self.conv1.kernel_size[0]
-        if x.is_cuda and x.dtype == torch.float16 and x.shape[-1] % ps == 0 and (3 * ps * ps) % 64 == 0:
+        if x.dim() == 6:
+            # patch-major crops (N, grid, grid, 3, ps, ps) straight from ops.crop_resize_normalize(patch=ps): already
+            # the unfolded operand of the patch-embedding GEMM
+            n, g = x.shape[0], x.shape[1]
+            assert x.shape[2] == g and x.shape[3:] == (3, ps, ps) and x.is_contiguous()
+            x = _linear(x.view(n * g * g, 3 * ps * ps), self.conv1.weight.view(self.conv1.weight.shape[0], -1),
+                        None).view(n, g * g, -1)
+        elif x.is_cuda and x.dtype == torch.float16 and x.shape[-1] % ps == 0 and (3 * ps * ps) % 64 == 0:
             # the patch embedding (kernel = stride = patch size, no bias) is a GEMM over unfolded patches
             n, c, hh, ww = x.shape
             g = hh // ps

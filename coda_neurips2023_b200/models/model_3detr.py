@@ -386,8 +386,15 @@ class Model3DETRPredictedBoxDistillationHead(nn.Module):
             vd = vd & chosen
         vd = vd.reshape(-1)
         scene = torch.arange(bsz, device=boxes.device, dtype=torch.int32).repeat_interleave(nsel)
+        extra = {}
+        visual = getattr(self.clip_model, "visual", None)
+        if (inputs["input_image"].is_cuda and self.clip_model.dtype == torch.float16
+                and isinstance(visual, clip_mod.model.VisionTransformer)):
+            ps = visual.conv1.kernel_size[0]
+            if self.clip_resolution % ps == 0 and (3 * ps * ps) % 64 == 0:
+                extra["patch"] = ps        # crops come out as the unfolded patches the ViT's first GEMM reads
         crops = ops.crop_resize_normalize(inputs["input_image"], scene, bx, vd, self.clip_resolution,
-                                          dtype=self.clip_model.dtype)
+                                          dtype=self.clip_model.dtype, **extra)
         feats = self.clip_model.encode_image(crops)
         if isinstance(feats, tuple):
             feats = feats[0]

@@ -807,10 +807,12 @@ CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
 @torch.no_grad()
 def crop_resize_normalize(images: torch.Tensor, scene: torch.Tensor, boxes: torch.Tensor, valid: torch.Tensor,
-                          res: int, dtype=torch.float16, mean=CLIP_MEAN, std=CLIP_STD) -> torch.Tensor:
+                          res: int, dtype=torch.float16, mean=CLIP_MEAN, std=CLIP_STD, patch: int = 0,
+                          tile_rows: int = 0) -> torch.Tensor:
     """images (B, H, W, 3) uint8, scene (N,) int32, boxes (N, 4) int32 [xmin, ymin, xmax, ymax],
     valid (N,) bool -> (N, 3, res, res) CLIP-normalised crops (white-padded to square, antialiased
-    bicubic resize with torchvision's uint8 semantics)."""
+    bicubic resize with torchvision's uint8 semantics); with patch = ps > 0 the crops come out patch-major,
+    (N, res / ps, res / ps, 3, ps, ps): the operand of the ViT's patch-embedding GEMM, no unfold copy."""
     _need_cuda(images, "crop_resize_normalize")
     if images.dtype != torch.uint8:
         raise RuntimeError("images must be uint8 (HWC)")
@@ -822,13 +824,18 @@ def crop_resize_normalize(images: torch.Tensor, scene: torch.Tensor, boxes: torc
     vd = valid.to(torch.uint8).contiguous()
     if dtype not in (torch.float16, torch.float32):
         raise RuntimeError("output dtype must be float16 or float32")
-    out = torch.empty((n, 3, res, res), dtype=dtype, device=img.device)
+    if patch > 0:
+        assert res % patch == 0
+        out = torch.empty((n, res // patch, res // patch, 3, patch, patch), dtype=dtype, device=img.device)
+    else:
+        out = torch.empty((n, 3, res, res), dtype=dtype, device=img.device)
+    work = torch.empty(nimg * h * w, dtype=torch.int32, device=img.device)      # RGBX copy of the images
     m = (ctypes.c_float * 3)(*mean)
     s = (ctypes.c_float * 3)(*std)
     with torch.cuda.device(img.device):
-        st = lib().coda_crop_resize_normalize(_i(nimg), _i(h), _i(w), _i(n), _i(res), ptr(img), ptr(sc), ptr(bx),
-                                              ptr(vd), m, s, _i(1 if dtype == torch.float16 else 0), ptr(out),
-                                              stream_of(img))
+        st = lib().coda_crop_resize_normalize_ex(_i(nimg), _i(h), _i(w), _i(n), _i(res), ptr(img), ptr(sc), ptr(bx),
+                                                 ptr(vd), m, s, _i(1 if dtype == torch.float16 else 0), _i(patch),
+                                                 _i(tile_rows), ptr(work), ptr(out), stream_of(img))
     check(st, "crop_resize_normalize")
     return out
 

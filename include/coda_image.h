@@ -26,13 +26,24 @@ extern "C" {
  *   boxes    (ncrops, 4) int32  xmin, ymin, xmax, ymax in pixels (already clipped to the image)
  *   valid    (ncrops) uint8   0 -> the crop is written as zeros
  *   mean/std (3) host floats
- *   out      (ncrops, 3, res, res), fp16 if out_half else fp32
+ *   out      fp16 if out_half else fp32;  patch == 0: (ncrops, 3, res, res);  patch == ps > 0 (res % ps == 0):
+ *            patch-major (ncrops, res / ps, res / ps, 3, ps, ps) -- row (crop, gy, gx) of this buffer is the unfolded
+ *            ps x ps patch the ViT's patch-embedding GEMM reads (CLIP/clip/model.py:612-625 conv1 with
+ *            kernel = stride = ps), so no unfold copy follows
+ *   workspace  coda_crop_resize_workspace_bytes(nimg, h, w) bytes: an RGBX copy of the images (one 32-bit load per
+ *            filter tap instead of three byte loads)
+ *   tile_rows  0 = automatic; output rows per CTA (tuning / tests)
+ *
+ * The resize is evaluated in its separable form -- a CTA resamples the source rows of its output rows horizontally
+ * into shared memory, then vertically -- with the sums in the order of the direct double loop (same bits).
  */
-int coda_crop_resize_normalize(int nimg, int h, int w, int ncrops, int res,
-                               const unsigned char *images, const int *scene,
-                               const int *boxes, const unsigned char *valid,
-                               const float *mean, const float *std, int out_half,
-                               void *out, void *stream);
+long long coda_crop_resize_workspace_bytes(int nimg, int h, int w);
+int coda_crop_resize_normalize_ex(int nimg, int h, int w, int ncrops, int res,
+                                  const unsigned char *images, const int *scene,
+                                  const int *boxes, const unsigned char *valid,
+                                  const float *mean, const float *std, int out_half,
+                                  int patch, int tile_rows, void *workspace, void *out,
+                                  void *stream);
 
 #ifdef __cplusplus
 }

@@ -175,6 +175,38 @@ def test_crop_resize_normalize_vs_torchvision_sequence():
     assert (out[6] == 0).all()
     half = ops.crop_resize_normalize(imgs, scene.cuda(), boxes.cuda(), valid.cuda(), 224, dtype=torch.float16)
     torch.testing.assert_close(half.float(), out, rtol=2e-3, atol=2e-3)
+    # the tile height of the separable kernel does not change a bit; patch-major output = the same pixels unfolded
+    for tr in (1, 4, 8):
+        again = ops.crop_resize_normalize(imgs, scene.cuda(), boxes.cuda(), valid.cuda(), 224, dtype=torch.float32,
+                                          tile_rows=tr)
+        assert torch.equal(again, out), tr
+    pm = ops.crop_resize_normalize(imgs, scene.cuda(), boxes.cuda(), valid.cuda(), 224, dtype=torch.float32, patch=32)
+    assert pm.shape == (7, 7, 7, 3, 32, 32)
+    assert torch.equal(pm, out.view(7, 3, 7, 32, 7, 32).permute(0, 2, 4, 1, 3, 5))
+
+
+def test_crop_resize_small_resolution_and_many_crops():
+    """a resolution that is not a multiple of the tile height, crops of every aspect, 300 crops in one launch:
+    against the reference's torchvision sequence within one LSB"""
+    rng = np.random.default_rng(3)
+    imgs = torch.from_numpy(rng.integers(0, 256, size=(3, 120, 160, 3), dtype=np.uint8)).cuda()
+    n = 300
+    x0 = rng.integers(0, 150, n); y0 = rng.integers(0, 110, n)
+    x1 = np.minimum(x0 + rng.integers(1, 160, n), 160); y1 = np.minimum(y0 + rng.integers(1, 120, n), 120)
+    boxes = torch.from_numpy(np.stack([x0, y0, x1, y1], 1).astype(np.int32))
+    scene = torch.from_numpy(rng.integers(0, 3, n).astype(np.int32))
+    valid = torch.from_numpy(rng.random(n) > 0.1)
+    res = 36
+    out = ops.crop_resize_normalize(imgs, scene.cuda(), boxes.cuda(), valid.cuda(), res, dtype=torch.float32)
+    mean = torch.tensor(ops.CLIP_MEAN, device="cuda").view(3, 1, 1)
+    std = torch.tensor(ops.CLIP_STD, device="cuda").view(3, 1, 1)
+    for i in range(0, n, 7):
+        if not bool(valid[i]):
+            assert (out[i] == 0).all()
+            continue
+        u8 = ref_crop.torchvision_sequence(imgs[int(scene[i])], [int(v) for v in boxes[i]], res)
+        exp = (u8 / 255.0 - mean) / std
+        assert ((out[i] - exp).abs() * std * 255.0).max() <= 1.01, f"crop {i}"
 
 
 def test_clip_image_tower_fp16_kernels_vs_fp32_math():
