@@ -168,7 +168,7 @@ def run_reference(a):
         "reference_scope": "ONE CPU process on this box's host cores, whatever --gpus says: the CPU path does not shard; "
                            "compare an N-GPU line with this value as is (it is not scaled by N)",
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------- our arm
@@ -450,7 +450,7 @@ def run_ours(a):
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"1 scene, 1 full step ({sec:.1f} s): reference PyTorch CPU arithmetic + "
                                           "C restatement of its CUDA-only ops; use --impl reference for more steps"}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     _finish(world, device)
 
 
@@ -464,8 +464,28 @@ def _finish(world, device):
         os._exit(0)
 
 
+_RESULT_FD = None
+
+
+def _emit(line: dict) -> None:
+    """the ONE JSON line, on the process's real stdout"""
+    text = json.dumps(line) + "\n"
+    if _RESULT_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, text.encode())
+
+
 def main():
+    global _RESULT_FD
     a = parse()
+    # stdout carries the result line and nothing else: native libraries print there too (NCCL's
+    # "NCCL version ..." banner under NCCL_DEBUG=VERSION), so file descriptor 1 is pointed at stderr for the
+    # duration of the run and the result is written to a private duplicate of the original descriptor
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:
