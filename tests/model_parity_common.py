@@ -162,7 +162,7 @@ def compare(model, out, loss, loss_dict, golden, rtol, atol, check_grads=True, g
         if f"aux{i}.text_correlation_embedding" in golden.files:
             chk(f"aux{i}.text_correlation_embedding", aux["text_correlation_embedding"], np.s_[:, ::4, ::8])
     exp_loss = float(golden["loss"])
-    errs["loss"] = abs(float(loss) - exp_loss) / abs(exp_loss)
+    errs["loss"] = abs(float(loss.detach()) - exp_loss) / abs(exp_loss)
     assert errs["loss"] <= rtol, f"loss {float(loss)} vs {exp_loss}"
     if "pseudo.count" in golden.files:
         # stage-2 discovery: the pseudo-label rows each scene's .npy file receives (reference :1524-1540)
