@@ -484,8 +484,11 @@ def main():
     # "NCCL version ..." banner under NCCL_DEBUG=VERSION), so file descriptor 1 is pointed at stderr for the
     # duration of the run and the result is written to a private duplicate of the original descriptor
     sys.stdout.flush()
-    _RESULT_FD = os.dup(1)
-    os.dup2(2, 1)
+    try:
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+    except OSError:          # no usable stderr / stdout descriptors: print the line the plain way
+        _RESULT_FD = None
     if a.impl == "reference":
         run_reference(a)
     else:
